@@ -1,0 +1,192 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_import.py shims) on CPU in the build container.
+
+    python tests/golden/make_golden.py --stage assets   # weights + scenes  (seconds)
+    python tests/golden/make_golden.py --stage small    # operator / f / solver vectors on crops (~2 min)
+    python tests/golden/make_golden.py --stage full     # full 256x256x8 reconstructions (~40 min CPU)
+
+The reference cannot travel to the GPU box, the fixtures do.  The reference ships no golden
+vectors of its own, so these files are the parity pin for oracle/deqsci_oracle.py
+and for the CUDA path.  ffdnet.ckpt is a missing blob in the mount; the FFDNet weights here are
+the reference's own networks/ffdnet/models/net_gray.pth (same architecture), re-keyed — the
+stand-in named in SURVEY.md F2.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+
+DENOISERS = ["ffdnet", "SimpleCNN", "RealSN_SimpleCNN"]
+WEIGHT_FILE = {"ffdnet": "weights_ffdnet_gray.npz", "SimpleCNN": "weights_cnn.npz",
+               "RealSN_SimpleCNN": "weights_rsn_cnn.npz"}
+SCENES = ["drop8", "runner8", "traffic"]
+CROP = (slice(96, 160), slice(96, 160))
+
+
+def stage_assets():
+    import scipy.io as sio
+    for d in DENOISERS:
+        sd = ref_import.reference_state_dict(d)
+        out = {}
+        for k, v in sd.items():
+            if k.endswith("weight_u"):          # power-iteration probe: training only, 1.2 MB
+                out["shape::" + k] = np.array(v.shape)
+                continue
+            out[k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, WEIGHT_FILE[d]), **out)
+        print(d, len(out), "tensors")
+    scenes = {}
+    for s in SCENES:
+        f = sio.loadmat(os.path.join(ref_import.REFERENCE_ROOT, "data/test_gray/%s_cacti.mat" % s))
+        mask, orig, meas = f["mask"], f["orig"], f["meas"]
+        assert mask.dtype == np.uint8 and set(np.unique(mask)) <= {0, 1}
+        assert orig.dtype == np.uint8
+        nm = meas.shape[2]
+        T = mask.shape[2]
+        # np.float32(meas) is exactly sum_t mask*orig (so it need not be stored)
+        for k in range(min(nm, orig.shape[2] // T)):
+            re = (mask.astype(np.float64) * orig[:, :, k * T:(k + 1) * T]).sum(2)
+            assert np.array_equal(np.float32(re), np.float32(meas[:, :, k])), (s, k)
+        scenes[s + "_mask_bits"] = np.packbits(mask.reshape(-1))
+        scenes[s + "_mask_shape"] = np.array(mask.shape)
+        scenes[s + "_orig"] = orig
+        scenes[s + "_nmeas"] = np.array(nm)
+        print(s, mask.shape, orig.shape, meas.shape, meas.dtype)
+    np.savez_compressed(os.path.join(HERE, "scenes.npz"), **scenes)
+
+
+def load_scene_ref(name):
+    """Loads a scene through the reference's own loader (utils/sci_dataloader.py:241-258)."""
+    ref_import.install_shims()
+    from utils.sci_dataloader import load_test_data
+    d = load_test_data(os.path.join(ref_import.REFERENCE_ROOT, "data/test_gray/%s_cacti.mat" % name))
+    return d["gt"], d["mask"], d["meas"]
+
+
+def stage_small():
+    ref_import.install_shims()
+    from utils.cg_utils import A_torch_, At_torch_, initial_point
+    out = {}
+    # (a) operator on seeded random inputs, incl. a grey (non-binary) mask and zero columns
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(2, 16, 12, 8, generator=g)
+    Phi = (torch.rand(2, 16, 12, 8, generator=g) < 0.5).float()
+    Phi[0, 3, 4] = 0
+    Phi[1] = torch.rand(16, 12, 8, generator=g)
+    y = A_torch_(x, Phi)
+    out["op_x"], out["op_Phi"], out["op_A"] = x.numpy(), Phi.numpy(), y.numpy()
+    out["op_At"] = At_torch_(y, Phi).numpy()
+    Phi_sum = torch.sum(Phi, axis=3)
+    Phi_sum[Phi_sum == 0] = 1
+    out["op_Phi_sum"] = Phi_sum.numpy()
+    out["op_x0"] = initial_point(y, Phi, Phi_sum, None).numpy()
+
+    # (b),(c) f calls and solver runs on a 64x64 crop of the traffic scene (B=1) and a B=2 batch
+    gt, mask, meas = load_scene_ref("traffic")
+    gt_c = torch.from_numpy(np.stack([gt[CROP][..., 0:8], gt[CROP][..., 8:16]]))      # [2,64,64,8]
+    Phi_c = torch.from_numpy(np.stack([mask[CROP], mask[CROP]]))
+    y_c = A_torch_(gt_c, Phi_c)
+    Phi_sum_c = torch.sum(Phi_c, axis=3)
+    Phi_sum_c[Phi_sum_c == 0] = 1
+    out["crop_gt"], out["crop_Phi"], out["crop_y"] = gt_c.numpy(), Phi_c.numpy(), y_c.numpy()
+    for d in DENOISERS:
+        solver, deq = ref_import.build_reference_deq(d, max_iter=30)
+        x0 = At_torch_(y_c, Phi_c)
+        with torch.no_grad():
+            f1 = solver(x0, y_c, Phi_c, Phi_sum_c)
+            f2 = solver(f1, y_c, Phi_c, Phi_sum_c)           # second call: sigma decayed once
+        out["f1_" + d], out["f2_" + d] = f1.numpy(), f2.numpy()
+        # solver trace with B=2 (alpha per sample, res over the whole batch)
+        solver, deq = ref_import.build_reference_deq(d, max_iter=30)
+        zin = []
+        h = solver.register_forward_pre_hook(lambda mod, args: zin.append(args[0].detach().clone()))
+        z = deq.forward(y_c, Phi_c, Phi_sum_c, initial_point=x0, train_flag=False)
+        h.remove()
+        out["deq30_z_" + d] = z.detach().numpy()
+        out["deq30_res_" + d] = np.array(deq.forward_res)
+        out["deq30_innorm_" + d] = np.array([float(t.norm()) for t in zin])
+        out["deq30_in10_" + d] = zin[10].numpy()
+        print(d, "ncalls", len(zin), "res", deq.forward_res)
+        # forward_iteration (Picard) for 6 steps, B=1
+        from solvers import new_equilibrium_utils_yaping as eq
+        solver, _ = ref_import.build_reference_deq(d, max_iter=30)
+        with torch.no_grad():
+            fz, res = eq.forward_iteration(lambda z: solver(z, y_c[:1], Phi_c[:1], Phi_sum_c[:1]),
+                                           x0[:1], max_iter=6, tol=1e-5)
+        out["picard6_z_" + d], out["picard6_res_" + d] = fz.numpy(), np.array(res)
+    # (d) SSIM / PSNR definitions
+    import pytorch_ssim
+    a = gt_c.permute(0, 3, 1, 2).contiguous()
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    out["ssim_a"], out["ssim_b"] = a.numpy(), b.numpy()
+    out["ssim_val"] = np.array(float(pytorch_ssim.ssim(a, b)))
+    out["psnr_val"] = np.array(ref_import.skimage_psnr(a.numpy(), b.numpy()))
+    np.savez_compressed(os.path.join(HERE, "small_vectors.npz"), **out)
+
+
+def stage_full(denoisers, scenes):
+    ref_import.install_shims()
+    import pytorch_ssim
+    from utils.cg_utils import At_torch_
+    path = os.path.join(HERE, "full_recon.npz")
+    out = dict(np.load(path)) if os.path.exists(path) else {}
+    for d in denoisers:
+        max_iter = 180 if d == "ffdnet" else 100       # test_ffdnet.sh:6 / entry default (:28)
+        for s in scenes:
+            gt, mask, meas = load_scene_ref(s)
+            nm = 1 if s in ("drop8", "runner8") else meas.shape[2]   # sci_equilibrium_training.py:167-168
+            Phi = torch.from_numpy(mask)[None]
+            Phi_sum = torch.sum(Phi, axis=3)
+            Phi_sum[Phi_sum == 0] = 1
+            for fi in range(nm):
+                key = "%s_%s_%d" % (d, s, fi)
+                if key + "_psnr" in out:
+                    continue
+                y = torch.from_numpy(meas[:, :, fi])[None]
+                g = torch.from_numpy(gt[:, :, fi * 8:(fi + 1) * 8])[None]
+                solver, deq = ref_import.build_reference_deq(d, max_iter=max_iter)
+                zin = []
+                h = solver.register_forward_pre_hook(lambda mod, args: zin.append(args[0].detach().clone()))
+                t0 = time.time()
+                z = deq.forward(y, Phi, Phi_sum, initial_point=At_torch_(y, Phi), train_flag=False)
+                dt = time.time() - t0
+                h.remove()
+                z = z.detach()
+                rec = z.clip(0, 1)
+                out[key + "_psnr"] = np.array(ref_import.skimage_psnr(g.numpy(), rec.numpy()))
+                out[key + "_ssim"] = np.array(float(pytorch_ssim.ssim(rec.permute(0, 3, 1, 2).contiguous(),
+                                                                        g.permute(0, 3, 1, 2).contiguous())))
+                out[key + "_res"] = np.array(deq.forward_res)
+                out[key + "_innorm"] = np.array([float(t.norm()) for t in zin])
+                out[key + "_seconds"] = np.array(dt)
+                out[key + "_ncalls"] = np.array(len(zin))
+                if fi == 0:
+                    for k in (2, 20, len(zin) - 2):
+                        out[key + "_in%d_crop" % k] = zin[k][0][CROP].numpy()
+                    out[key + "_z_crop"] = z[0][CROP].numpy()
+                print(key, "psnr %.4f ssim %.5f res %.3e calls %d  %.1fs" %
+                      (out[key + "_psnr"], out[key + "_ssim"], deq.forward_res, len(zin), dt), flush=True)
+                np.savez_compressed(path, **out)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full"])
+    ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
+    ap.add_argument("--scenes", nargs="*", default=SCENES)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    if a.stage == "assets":
+        stage_assets()
+    elif a.stage == "small":
+        stage_small()
+    else:
+        stage_full(a.denoisers, a.scenes)
