@@ -1,0 +1,72 @@
+"""ctypes binding of libdeqsci.so (include/deqsci.h).  There is NO fallback: if the CUDA library
+is missing or a call fails, the product path raises."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeqsci.so")
+
+NET_FFDNET, NET_DNCNN = 0, 1
+PREC_TC_SPLIT, PREC_FP32, PREC_TC_SINGLE = 0, 1, 2
+PRECISIONS = {"tc_split": PREC_TC_SPLIT, "fp32": PREC_FP32, "tc_single": PREC_TC_SINGLE}
+
+
+class DeqsciError(RuntimeError):
+    pass
+
+
+class ConvLayer(Structure):
+    _fields_ = [("cin", c_int), ("cout", c_int), ("relu", c_int),
+                ("weight_host", POINTER(c_float)), ("scale_host", POINTER(c_float)),
+                ("bias_host", POINTER(c_float))]
+
+
+# name -> (restype, argtypes); every symbol include/deqsci.h declares (tests check the list)
+_P = c_void_p
+SIGNATURES = {
+    "deqsci_version": (c_int, []),
+    "deqsci_last_error": (c_char_p, []),
+    "deqsci_gap_forward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_gap_adjoint": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_phi_sum": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_gap_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_gap_vjp": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_denoiser_create": (c_int, [c_int, c_int, c_int, POINTER(ConvLayer), POINTER(_P)]),
+    "deqsci_denoiser_destroy": (c_int, [_P]),
+    "deqsci_denoiser_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "deqsci_denoise_residual": (c_int, [_P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_iterate": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_anderson_scratch_floats": (c_size_t, [c_int, c_int, c_longlong]),
+    "deqsci_anderson_update": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, c_int,
+                                       c_float, c_float, _P]),
+    "deqsci_anderson_mix": (c_int, [_P, _P, _P, c_int, c_int, c_longlong, c_int, c_int, c_float, _P]),
+    "deqsci_residual": (c_int, [_P, _P, _P, _P, c_longlong, c_float, _P]),
+    "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libdeqsci.so once.  Raises DeqsciError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DeqsciError(
+                "libdeqsci.so is not built (%s). Run `python -m deqsci_b200.build` "
+                "(nvcc, sm_100a); there is no CPU or PyTorch fallback for the native path." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().deqsci_last_error()
+        raise DeqsciError("%s failed (status %d): %s" % (what or "libdeqsci call", status,
+                                                         msg.decode() if msg else "?"))

@@ -1,0 +1,230 @@
+// C-ABI glue: error text, the denoiser plan (weight packing / upload) and the layer sequencing of
+// deqsci_denoise_residual / deqsci_iterate.  See include/deqsci.h for the contract.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace deqsci {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// launchers implemented in conv_cc.cu / conv_tc.cu / gap.cu
+int conv_first_launch(int kind, bool fuse_gap, const float* zin, const float* y, const float* phi,
+                      const float* phi_sum, float* zprime_out, float sigma, const float* wpack,
+                      const float* scale, const float* bias, int relu, __half* act_out, long long plane_elems,
+                      int B, int H, int W, int T, cudaStream_t st);
+int conv_mid_fp32_launch(const __half* act_in, __half* act_out, long long plane_elems, const float* wpack,
+                         const float* scale, const float* bias, int relu, int NF, int Hc, int Wc, cudaStream_t st);
+int conv_last_launch(int kind, const __half* act_in, long long plane_elems, const float* wpack,
+                     const float* scale, const float* bias, int relu, const float* zprime, float* out, int B,
+                     int H, int W, int T, cudaStream_t st);
+int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long long plane_elems,
+                       const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                       cudaStream_t st);
+size_t tc_weight_image_bytes(bool split);
+void tc_pack_weights(const float* w, bool split, uint8_t* img);
+
+struct Layer {
+  int cin = 0, cout = 0, relu = 0;
+  float* w_cc = nullptr;      // CUDA-core packing [9][cin][cout] fp32
+  uint8_t* w_tc = nullptr;    // tcgen05 shared-memory image (hidden layers, TC modes)
+  float* scale = nullptr;     // [cout] or null
+  float* bias = nullptr;      // [cout] or null
+};
+
+}  // namespace deqsci
+
+struct deqsci_denoiser {
+  int kind = 0, precision = 0;
+  std::vector<deqsci::Layer> layers;
+};
+
+using namespace deqsci;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int deqsci_version(void) { return DEQSCI_VERSION; }
+extern "C" const char* deqsci_last_error(void) { return g_err; }
+
+extern "C" int deqsci_denoiser_destroy(deqsci_denoiser* h) {
+  if (!h) return DEQSCI_OK;
+  for (auto& L : h->layers) {
+    if (L.w_cc) cudaFree(L.w_cc);
+    if (L.w_tc) cudaFree(L.w_tc);
+    if (L.scale) cudaFree(L.scale);
+    if (L.bias) cudaFree(L.bias);
+  }
+  delete h;
+  return DEQSCI_OK;
+}
+
+static int upload(const void* host, size_t bytes, void** dev) {
+  DEQSCI_CUDA(cudaMalloc(dev, bytes));
+  DEQSCI_CUDA(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return DEQSCI_OK;
+}
+
+extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layers,
+                                      const deqsci_conv_layer* layers_host, deqsci_denoiser** out) {
+  DEQSCI_CHECK_ARG(out != nullptr && layers_host != nullptr, "denoiser_create: null pointer");
+  *out = nullptr;
+  DEQSCI_CHECK_ARG(net_kind == DEQSCI_NET_FFDNET || net_kind == DEQSCI_NET_DNCNN, "denoiser_create: net_kind=%d",
+                   net_kind);
+  DEQSCI_CHECK_ARG(precision >= DEQSCI_PREC_TC_SPLIT && precision <= DEQSCI_PREC_TC_SINGLE,
+                   "denoiser_create: precision=%d", precision);
+  DEQSCI_CHECK_ARG(num_layers >= 2 && num_layers <= 64, "denoiser_create: num_layers=%d (need 2..64)", num_layers);
+  const int cin0 = net_kind == DEQSCI_NET_FFDNET ? 5 : 1, coutL = net_kind == DEQSCI_NET_FFDNET ? 4 : 1;
+  for (int i = 0; i < num_layers; ++i) {
+    const deqsci_conv_layer& L = layers_host[i];
+    const int want_in = i == 0 ? cin0 : kHidden, want_out = i == num_layers - 1 ? coutL : kHidden;
+    DEQSCI_CHECK_ARG(L.cin == want_in && L.cout == want_out, "denoiser_create: layer %d is %d->%d, expected %d->%d",
+                     i, L.cin, L.cout, want_in, want_out);
+    DEQSCI_CHECK_ARG(L.weight_host != nullptr, "denoiser_create: layer %d has no weights", i);
+  }
+  if (precision != DEQSCI_PREC_FP32) {
+    int dev = 0, major = 0;
+    DEQSCI_CUDA(cudaGetDevice(&dev));
+    DEQSCI_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+      set_error("denoiser_create: tcgen05 precision modes need an sm_100 device (found sm_%d0)", major);
+      return DEQSCI_ERR_ARCH;
+    }
+  }
+  deqsci_denoiser* h = new deqsci_denoiser();
+  h->kind = net_kind;
+  h->precision = precision;
+  h->layers.resize(num_layers);
+  int rc = DEQSCI_OK;
+  for (int i = 0; i < num_layers && rc == DEQSCI_OK; ++i) {
+    const deqsci_conv_layer& S = layers_host[i];
+    Layer& L = h->layers[i];
+    L.cin = S.cin; L.cout = S.cout; L.relu = S.relu;
+    // [cout][cin][3][3] -> [tap][cin][cout]
+    std::vector<float> pk((size_t)9 * S.cin * S.cout);
+    for (int o = 0; o < S.cout; ++o)
+      for (int c = 0; c < S.cin; ++c)
+        for (int t = 0; t < 9; ++t) pk[((size_t)t * S.cin + c) * S.cout + o] = S.weight_host[((size_t)o * S.cin + c) * 9 + t];
+    rc = upload(pk.data(), pk.size() * sizeof(float), (void**)&L.w_cc);
+    if (rc == DEQSCI_OK && S.scale_host) rc = upload(S.scale_host, S.cout * sizeof(float), (void**)&L.scale);
+    if (rc == DEQSCI_OK && S.bias_host) rc = upload(S.bias_host, S.cout * sizeof(float), (void**)&L.bias);
+    const bool hidden = (i > 0 && i < num_layers - 1);
+    if (rc == DEQSCI_OK && hidden && precision != DEQSCI_PREC_FP32) {
+      const bool split = precision == DEQSCI_PREC_TC_SPLIT;
+      std::vector<uint8_t> img(tc_weight_image_bytes(split));
+      tc_pack_weights(S.weight_host, split, img.data());
+      rc = upload(img.data(), img.size(), (void**)&L.w_tc);
+    }
+  }
+  if (rc != DEQSCI_OK) {
+    deqsci_denoiser_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return DEQSCI_OK;
+}
+
+namespace {
+struct Geometry {
+  int SC, Hc, Wc, NF;
+  long long plane_elems;
+  size_t zprime_bytes, act_bytes;
+};
+int geometry(const deqsci_denoiser* h, int B, int H, int W, int T, Geometry* g) {
+  DEQSCI_CHECK_ARG(h != nullptr, "null denoiser handle");
+  DEQSCI_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0, "non-positive dimension B=%d H=%d W=%d T=%d", B, H, W, T);
+  DEQSCI_CHECK_ARG(B <= 65535, "B=%d exceeds 65535 per call", B);
+  g->SC = h->kind == DEQSCI_NET_FFDNET ? 2 : 1;
+  DEQSCI_CHECK_ARG(H % g->SC == 0 && W % g->SC == 0, "FFDNet needs even H and W (got %dx%d)", H, W);
+  g->Hc = H / g->SC;
+  g->Wc = W / g->SC;
+  g->NF = B * T;
+  g->plane_elems = (long long)g->NF * g->Hc * g->Wc * kHidden;
+  g->zprime_bytes = align_up((size_t)B * H * W * T * sizeof(float), 1024);
+  g->act_bytes = align_up((size_t)g->plane_elems * 2 * sizeof(__half), 1024);
+  return DEQSCI_OK;
+}
+}  // namespace
+
+extern "C" size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T) {
+  Geometry g;
+  if (geometry(h, B, H, W, T, &g) != DEQSCI_OK) return 0;
+  return 1024 + g.zprime_bytes + 2 * g.act_bytes;
+}
+
+static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, const float* y, const float* phi,
+                     const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes, int B,
+                     int H, int W, int T, void* stream) {
+  Geometry g;
+  int rc = geometry(h, B, H, W, T, &g);
+  if (rc) return rc;
+  DEQSCI_CHECK_ARG(z != nullptr && out != nullptr && workspace != nullptr, "null pointer");
+  if (fuse_gap) DEQSCI_CHECK_ARG(y && phi && phi_sum, "iterate: null y / phi / phi_sum");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const size_t need = (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + g.zprime_bytes + 2 * g.act_bytes;
+  if (workspace_bytes < need) {
+    set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+    return DEQSCI_ERR_WORKSPACE;
+  }
+  float* zprime_ws = reinterpret_cast<float*>(ws);
+  __half* act[2] = {reinterpret_cast<__half*>(ws + g.zprime_bytes),
+                    reinterpret_cast<__half*>(ws + g.zprime_bytes + g.act_bytes)};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nl = (int)h->layers.size();
+  const Layer& L0 = h->layers[0];
+  rc = conv_first_launch(h->kind, fuse_gap, z, y, phi, phi_sum, zprime_ws, sigma, L0.w_cc, L0.scale, L0.bias,
+                         L0.relu, act[0], g.plane_elems, B, H, W, T, st);
+  if (rc) return rc;
+  int cur = 0;
+  for (int i = 1; i < nl - 1; ++i) {
+    const Layer& L = h->layers[i];
+    if (h->precision == DEQSCI_PREC_FP32)
+      rc = conv_mid_fp32_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
+                                g.Wc, st);
+    else
+      rc = conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], act[cur ^ 1], g.plane_elems, L.w_tc,
+                              L.scale, L.bias, L.relu, g.NF, g.Hc, g.Wc, st);
+    if (rc) return rc;
+    cur ^= 1;
+  }
+  const Layer& LL = h->layers[nl - 1];
+  return conv_last_launch(h->kind, act[cur], g.plane_elems, LL.w_cc, LL.scale, LL.bias, LL.relu,
+                          fuse_gap ? zprime_ws : z, out, B, H, W, T, st);
+}
+
+extern "C" int deqsci_denoise_residual(const deqsci_denoiser* h, const float* zin, float sigma, float* out,
+                                       void* workspace, size_t workspace_bytes, int B, int H, int W, int T,
+                                       void* stream) {
+  return run_stack(h, false, zin, nullptr, nullptr, nullptr, sigma, out, workspace, workspace_bytes, B, H, W, T,
+                   stream);
+}
+
+extern "C" int deqsci_iterate(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                              const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
+                              int B, int H, int W, int T, void* stream) {
+  return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream);
+}
+
+// Testing hook (declared in deqsci.h): one hidden 64->64 layer on caller-provided planes.
+extern "C" int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* act_in, void* act_out,
+                                         int NF, int Hc, int Wc, void* stream) {
+  DEQSCI_CHECK_ARG(h && act_in && act_out, "debug_hidden_layer: null pointer");
+  DEQSCI_CHECK_ARG(layer > 0 && layer < (int)h->layers.size() - 1, "debug_hidden_layer: layer %d is not hidden", layer);
+  DEQSCI_CHECK_ARG(NF > 0 && Hc > 0 && Wc > 0, "debug_hidden_layer: bad shape");
+  const Layer& L = h->layers[layer];
+  const long long plane = (long long)NF * Hc * Wc * kHidden;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == DEQSCI_PREC_FP32)
+    return conv_mid_fp32_launch((const __half*)act_in, (__half*)act_out, plane, L.w_cc, L.scale, L.bias, L.relu, NF,
+                                Hc, Wc, st);
+  return conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, (const __half*)act_in, (__half*)act_out, plane,
+                            L.w_tc, L.scale, L.bias, L.relu, NF, Hc, Wc, st);
+}

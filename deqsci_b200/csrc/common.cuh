@@ -1,0 +1,63 @@
+// Shared host/device helpers for libdeqsci (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/deqsci.h"
+
+namespace deqsci {
+
+// thread-local error text behind deqsci_last_error()
+void set_error(const char* fmt, ...);
+
+#define DEQSCI_CHECK_ARG(cond, ...)                  \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ::deqsci::set_error(__VA_ARGS__);              \
+      return DEQSCI_ERR_INVALID;                     \
+    }                                                \
+  } while (0)
+
+#define DEQSCI_CUDA(call)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ::deqsci::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                          __FILE__, __LINE__);                                         \
+      return DEQSCI_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define DEQSCI_LAUNCH_CHECK() DEQSCI_CUDA(cudaGetLastError())
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Activation storage between conv layers: channels-last [frames, H, W, 64], each value stored as
+// an fp16 pair  v ~= hi + lo * 2^-11  in two planes (hi plane then lo plane).  Keeps ~22 mantissa
+// bits (this split reproduces the fp32 trajectory at its noise floor) in exactly
+// the operand format the tcgen05 kind::f16 MMA consumes.
+constexpr int kHidden = 64;
+constexpr float kLoScale = 2048.0f;           // 2^11
+constexpr float kLoInvScale = 1.0f / 2048.0f;
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+}
+__device__ __forceinline__ float join_f16(__half hi, __half lo) {
+  return fmaf(__half2float(lo), kLoInvScale, __half2float(hi));
+}
+
+}  // namespace deqsci

@@ -1,0 +1,408 @@
+// Kernel group 2b: hidden 3x3 conv layers (64 -> 64 channels) as a tcgen05 / TMEM implicit GEMM
+// fed by TMA (sm_100a only).
+//
+// GEMM view per layer:  D[M = pixels, N = 64 cout] = sum over 9 taps of  A_tap[M, 64 cin] * W_tap[64 cin, N]
+//   A_tap is the channels-last activation tile shifted by (ky-1, kx-1): one 4-D TMA box
+//   {64 ch, TWm, THm, 1 frame} per tap, zero padding = TMA out-of-bounds fill, frames never mix.
+//   One CTA tile = 128 pixels (UMMA_M = 128, cta_group::1), K per tap = 64 = one 128-byte swizzle row.
+//
+// Precision (the parity mode, DEQSCI_PREC_TC_SPLIT): activations and weights are fp16 pairs
+//   v = hi + lo' * 2^-11.  D = Ah*Wh + 2^-11 (Ah*Wl' + Al'*Wh) with fp32 accumulation in TMEM:
+//     MMA 1: A = Ah, B = [Wh | Wl'] (N = 128)  -> columns [0,64) main, [64,128) correction
+//     MMA 2: A = Al', B = Wh        (N =  64)  -> accumulates into the correction columns
+//   i.e. 3 products for 2 instructions (the dropped Al*Wl term is O(2^-22)).  The epilogue combines
+//   main + 2^-11 * correction, applies the folded-BatchNorm affine + ReLU and re-splits to hi/lo.
+//
+// Warp roles (192 threads, persistent over tiles, one CTA per SM):
+//   warp 0    : TMA producer (weights once via 1-D bulk copies; per tap the hi and lo A boxes)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5 : epilogue (tcgen05.ld -> affine/ReLU/split -> global stores), one TMEM lane quarter each
+// Pipelines: smem A ring (full/empty mbarriers, tcgen05.commit frees a slot) and a double-buffered
+// TMEM accumulator (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>   // CUtensorMap types only; the encode entry point is fetched at run time
+
+#include "common.cuh"
+
+namespace deqsci {
+
+constexpr int kTileM = 128;
+constexpr int kTapBytesA = kTileM * 128;        // 16 KB: 128 pixels x 64 fp16
+constexpr int kTcThreads = 192;
+
+template <bool SPLIT>
+struct TcCfg {
+  static constexpr int kBRows = SPLIT ? 128 : 64;             // rows of the B tile per tap
+  static constexpr int kTapBytesB = kBRows * 128;             // 16 KB / 8 KB
+  static constexpr int kWBytes = 9 * kTapBytesB;              // 144 KB / 72 KB
+  static constexpr int kStageBytes = SPLIT ? 2 * kTapBytesA : kTapBytesA;
+  static constexpr int kStages = SPLIT ? 2 : 6;
+  static constexpr int kAccCols = SPLIT ? 128 : 64;           // TMEM columns per accumulator buffer
+  static constexpr int kTmemCols = 2 * kAccCols;              // 256 / 128 (power of two >= 32)
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kWBytes + kStages * kStageBytes + 1024 /*barriers, affine*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a pipeline bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO=1024B | version 1 (sm_100) | layout 2
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  const uint8_t* wimg;      // pre-swizzled weight image, TcCfg::kWBytes
+  const float* scale;       // [64] or null
+  const float* bias;        // [64] or null
+  __half* out_hi;           // output planes (channels-last)
+  __half* out_lo;
+  int relu;
+  int NF, Hc, Wc;
+  int TWm, THm;             // tile = THm rows x TWm cols, TWm*THm == 128
+  int tiles_x, tiles_y;
+  long long n_tiles;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                   const TcParams p) {
+  using Cfg = TcCfg<SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + Cfg::kWBytes;
+  uint8_t* tail = a_s + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);       // [0] w_full, then full[S], empty[S], tfull[2], tempty[2]
+  float* aff_s = reinterpret_cast<float*>(tail + 256);      // scale[64], bias[64]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + Cfg::kStages + s]); };
+  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * Cfg::kStages + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[3 + 2 * Cfg::kStages + b]); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int c = threadIdx.x - 64;
+    aff_s[c] = p.scale ? p.scale[c] : 1.f;
+    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, Cfg::kWBytes);
+      for (int t = 0; t < 9; ++t)
+        bulk_load_1d(smem_u32(w_s + t * Cfg::kTapBytesB), p.wimg + (size_t)t * Cfg::kTapBytesB, Cfg::kTapBytesB, bar_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        const int nf = (int)(tile / per_frame);
+        const int rem = (int)(tile - (long long)nf * per_frame);
+        const int h0 = (rem / p.tiles_x) * p.THm, w0 = (rem % p.tiles_x) * p.TWm;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_arrive_expect_tx(bar_full(stage), Cfg::kStageBytes);
+          const uint32_t dst = smem_u32(a_s + stage * Cfg::kStageBytes);
+          tma_load_4d(dst, &map_hi, bar_full(stage), 0, w0 + kx - 1, h0 + ky - 1, nf);
+          if (SPLIT) tma_load_4d(dst + kTapBytesA, &map_lo, bar_full(stage), 0, w0 + kx - 1, h0 + ky - 1, nf);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = make_idesc(kTileM, SPLIT ? 128 : 64);
+      constexpr uint32_t idesc_lo = make_idesc(kTileM, 64);
+      mbar_wait(bar_w, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t tphase = 0;
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty(buf), tphase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + buf * Cfg::kAccCols;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(bar_full(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_s + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = make_sdesc(a_addr);
+          const uint64_t a_lo = make_sdesc(a_addr + kTapBytesA);
+          const uint64_t b_w = make_sdesc(smem_u32(w_s + tap * Cfg::kTapBytesB));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {               // K = 64 per tap = 4 x UMMA_K(16); +32 bytes per step
+            umma_f16(d_main, a_hi + 2 * k, b_w + 2 * k, idesc_main, (tap | k) != 0);
+            if (SPLIT) umma_f16(d_main + 64, a_lo + 2 * k, b_w + 2 * k, idesc_lo, 1u);
+          }
+          umma_commit(bar_empty(stage));              // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull(buf));                  // accumulator complete -> epilogue
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                     // TMEM lanes [32*quarter, 32*quarter+32)
+    const int m = quarter * 32 + lane;                // pixel row of the tile owned by this thread
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int per_frame = p.tiles_x * p.tiles_y;
+      const int nf = (int)(tile / per_frame);
+      const int rem = (int)(tile - (long long)nf * per_frame);
+      const int h = (rem / p.tiles_x) * p.THm + m / p.TWm;
+      const int w = (rem % p.tiles_x) * p.TWm + m % p.TWm;
+      const bool inside = (h < p.Hc && w < p.Wc);
+      const long long off = (((long long)nf * p.Hc + h) * p.Wc + w) * 64;
+      mbar_wait(bar_tfull(buf), tphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Cfg::kAccCols;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {          // 32 output channels at a time
+        uint32_t acc[32], cor[32];
+        tmem_ld32(t_addr + half * 32, acc);
+        if (SPLIT) tmem_ld32(t_addr + 64 + half * 32, cor);
+        tmem_ld_wait();
+        uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float v[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = half * 32 + e + u;
+            float a = __uint_as_float(acc[e + u]);
+            if (SPLIT) a = fmaf(__uint_as_float(cor[e + u]), kLoInvScale, a);
+            a = fmaf(a, aff_s[c], aff_s[64 + c]);
+            v[u] = p.relu ? fmaxf(a, 0.f) : a;
+          }
+          __half h0, l0, h1, l1;
+          split_f16(v[0], h0, l0);
+          split_f16(v[1], h1, l1);
+          hi_pk[e >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lo_pk[e >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        if (inside) {
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off + half * 32);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off + half * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dh[q] = make_uint4(hi_pk[4 * q], hi_pk[4 * q + 1], hi_pk[4 * q + 2], hi_pk[4 * q + 3]);
+            dl[q] = make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(buf));    // 4 arrivals (one per epilogue warp) free the buffer
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+void tc_tile_shape(int Wc, int* TWm, int* THm) {
+  int tw = 128;
+  while (tw > 8 && tw / 2 >= Wc) tw /= 2;     // smallest power of two >= Wc, clamped to [8,128]
+  *TWm = tw;
+  *THm = kTileM / tw;
+}
+
+static int make_act_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int TWm, int THm) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
+  cuuint64_t strides[3] = {128, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)TWm, (cuuint32_t)THm, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
+  return DEQSCI_OK;
+}
+
+size_t tc_weight_image_bytes(bool split) { return split ? TcCfg<true>::kWBytes : TcCfg<false>::kWBytes; }
+
+// Host packing of one hidden layer: w [64 cout][64 cin][3][3] fp32 -> the exact shared-memory image
+// the kernel bulk-copies: per tap a K-major tile [rows n][64 k=cin] fp16 with the 128-byte swizzle
+// (16-byte chunk index XOR (row & 7)); rows [0,64) = hi(W), rows [64,128) = lo'(W) (split mode).
+void tc_pack_weights(const float* w, bool split, uint8_t* img) {
+  const int rows = split ? 128 : 64;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    for (int n = 0; n < rows; ++n) {
+      const int co = n & 63;
+      for (int k = 0; k < 64; ++k) {
+        const float v = w[((co * 64 + k) * 3 + ky) * 3 + kx];
+        const __half hi = __float2half_rn(v);
+        __half val = hi;
+        if (n >= 64) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
+        const size_t byte = (size_t)tap * rows * 128 + (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) +
+                            (size_t)(k & 7) * 2;
+        *reinterpret_cast<__half*>(img + byte) = val;
+      }
+    }
+  }
+}
+
+int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long long plane_elems,
+                       const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                       cudaStream_t st) {
+  int TWm, THm;
+  tc_tile_shape(Wc, &TWm, &THm);
+  CUtensorMap map_hi, map_lo;
+  int rc = make_act_map(&map_hi, act_in, NF, Hc, Wc, TWm, THm);
+  if (rc) return rc;
+  rc = make_act_map(&map_lo, act_in + plane_elems, NF, Hc, Wc, TWm, THm);
+  if (rc) return rc;
+  TcParams p;
+  p.wimg = wimg; p.scale = scale; p.bias = bias;
+  p.out_hi = act_out; p.out_lo = act_out + plane_elems;
+  p.relu = relu; p.NF = NF; p.Hc = Hc; p.Wc = Wc; p.TWm = TWm; p.THm = THm;
+  p.tiles_x = (Wc + TWm - 1) / TWm;
+  p.tiles_y = (Hc + THm - 1) / THm;
+  p.n_tiles = (long long)NF * p.tiles_x * p.tiles_y;
+  const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+  if (split) {
+    DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<true>::kSmemBytes));
+    conv_mid_tc_kernel<true><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(map_hi, map_lo, p);
+  } else {
+    DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<false>::kSmemBytes));
+    conv_mid_tc_kernel<false><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(map_hi, map_lo, p);
+  }
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+}  // namespace deqsci

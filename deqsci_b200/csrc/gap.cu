@@ -1,0 +1,178 @@
+// Kernel group 1: SCI operator and fused GAP data-consistency step (HBM-bound, fp32).
+//
+// Layout (reference): cube [B,H,W,T] with T innermost, snapshot [B,H,W].  For T == 8 a pixel's
+// 8 frames are 32 contiguous bytes: two adjacent lanes take one float4 each, so every warp-wide
+// load/store is a fully coalesced 512-byte access, and the 8-term sum over T finishes with a
+// single shuffle.  Any other T uses one thread per pixel.
+//
+// Algorithmic bytes per pixel (T=8, fp32): read z 32 + Phi 32 + y 4 + phi_sum 4, write 32 = 104.
+// Multiplications and additions are kept as separate roundings (no FMA contraction) to follow the
+// reference's `x*Phi` -> sum, `y - fb`, `/ Phi_sum`, `y[...,None]*Phi`, `z + ...` sequence
+// (utils/cg_utils.py:90,129; solvers/equilibrium_solvers_yaping.py:399-400).
+#include "common.cuh"
+
+namespace deqsci {
+
+enum GapOp { OP_FORWARD = 0, OP_ADJOINT = 1, OP_STEP = 2, OP_VJP = 3, OP_PHISUM = 4 };
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float dot4_nofma(float4 a, float4 b) {
+  float s = __fmul_rn(a.x, b.x);
+  s = __fadd_rn(s, __fmul_rn(a.y, b.y));
+  s = __fadd_rn(s, __fmul_rn(a.z, b.z));
+  s = __fadd_rn(s, __fmul_rn(a.w, b.w));
+  return s;
+}
+
+// T == 8: item = half pixel (4 frames); lanes 2k and 2k+1 share a pixel.
+template <int OP>
+__global__ void __launch_bounds__(256) gap_t8_kernel(const float* __restrict__ a,      // z / x / v (cube) or y for ADJOINT
+                                                     const float* __restrict__ y,      // snapshot (STEP)
+                                                     const float* __restrict__ phi,
+                                                     const float* __restrict__ phi_sum,
+                                                     const float* __restrict__ add,    // VJP optional addend
+                                                     float* __restrict__ out, long long n_items) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // Warp-uniform trip count: every lane of a warp runs the same number of iterations so the
+  // full-mask shuffles are always convergent; lanes past the end recompute the last pair (n_items
+  // is even, so a lane and its partner i^1 are clamped together) and store nothing.
+  const long long first = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (long long base = first; base < n_items; base += stride) {
+    long long i = base + (threadIdx.x & 31);
+    const bool valid = i < n_items;          // clamped lanes compute but never store
+    if (!valid) i = n_items - 2 + (i & 1);
+    const long long pix = i >> 1;
+    const float4 p = ldg4(phi + i * 4);
+    if (OP == OP_ADJOINT) {
+      const float yy = __ldg(a + pix);
+      float4 o;
+      o.x = __fmul_rn(yy, p.x); o.y = __fmul_rn(yy, p.y); o.z = __fmul_rn(yy, p.z); o.w = __fmul_rn(yy, p.w);
+      if (valid) *reinterpret_cast<float4*>(out + i * 4) = o;
+      continue;
+    }
+    if (OP == OP_PHISUM) {
+      float s = __fadd_rn(__fadd_rn(p.x, p.y), __fadd_rn(p.z, p.w));
+      s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+      if (valid && (i & 1) == 0) out[pix] = (s == 0.0f) ? 1.0f : s;
+      continue;
+    }
+    const float4 zv = ldg4(a + i * 4);
+    float s = dot4_nofma(zv, p);
+    const float other = __shfl_xor_sync(0xffffffffu, s, 1);
+    // same association on both lanes: (frames 0-3) + (frames 4-7)
+    s = (i & 1) ? __fadd_rn(other, s) : __fadd_rn(s, other);
+    if (OP == OP_FORWARD) {
+      if (valid && (i & 1) == 0) out[pix] = s;
+      continue;
+    }
+    float r;
+    if (OP == OP_STEP) r = __fdiv_rn(__fsub_rn(__ldg(y + pix), s), __ldg(phi_sum + pix));
+    else               r = -__fdiv_rn(s, __ldg(phi_sum + pix));
+    float4 o;
+    o.x = __fadd_rn(zv.x, __fmul_rn(r, p.x));
+    o.y = __fadd_rn(zv.y, __fmul_rn(r, p.y));
+    o.z = __fadd_rn(zv.z, __fmul_rn(r, p.z));
+    o.w = __fadd_rn(zv.w, __fmul_rn(r, p.w));
+    if (OP == OP_VJP && add != nullptr) {
+      const float4 ad = ldg4(add + i * 4);
+      o.x = __fadd_rn(o.x, ad.x); o.y = __fadd_rn(o.y, ad.y); o.z = __fadd_rn(o.z, ad.z); o.w = __fadd_rn(o.w, ad.w);
+    }
+    if (valid) *reinterpret_cast<float4*>(out + i * 4) = o;
+  }
+}
+
+// any T: one thread per pixel
+template <int OP>
+__global__ void __launch_bounds__(256) gap_generic_kernel(const float* __restrict__ a, const float* __restrict__ y,
+                                                          const float* __restrict__ phi,
+                                                          const float* __restrict__ phi_sum,
+                                                          const float* __restrict__ add, float* __restrict__ out,
+                                                          long long n_pix, int T) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += stride) {
+    const float* pp = phi + pix * T;
+    if (OP == OP_ADJOINT) {
+      const float yy = a[pix];
+      for (int t = 0; t < T; ++t) out[pix * T + t] = __fmul_rn(yy, pp[t]);
+      continue;
+    }
+    if (OP == OP_PHISUM) {
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) s = __fadd_rn(s, pp[t]);
+      out[pix] = (s == 0.0f) ? 1.0f : s;
+      continue;
+    }
+    const float* zp = a + pix * T;
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s = __fadd_rn(s, __fmul_rn(zp[t], pp[t]));
+    if (OP == OP_FORWARD) { out[pix] = s; continue; }
+    float r;
+    if (OP == OP_STEP) r = __fdiv_rn(__fsub_rn(y[pix], s), phi_sum[pix]);
+    else               r = -__fdiv_rn(s, phi_sum[pix]);
+    for (int t = 0; t < T; ++t) {
+      float o = __fadd_rn(zp[t], __fmul_rn(r, pp[t]));
+      if (OP == OP_VJP && add != nullptr) o = __fadd_rn(o, add[pix * T + t]);
+      out[pix * T + t] = o;
+    }
+  }
+}
+
+template <int OP>
+static int launch_gap(const float* a, const float* y, const float* phi, const float* phi_sum, const float* add,
+                      float* out, int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0, "gap: non-positive dimension B=%d H=%d W=%d T=%d", B, H, W, T);
+  DEQSCI_CHECK_ARG(phi != nullptr && out != nullptr, "gap: null pointer");
+  if (OP != OP_PHISUM) DEQSCI_CHECK_ARG(a != nullptr, "gap: null input");
+  if (OP == OP_STEP) DEQSCI_CHECK_ARG(y != nullptr && phi_sum != nullptr, "gap_step: null y / phi_sum");
+  if (OP == OP_VJP) DEQSCI_CHECK_ARG(phi_sum != nullptr, "gap_vjp: null phi_sum");
+  const long long n_pix = (long long)B * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 256;
+  // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM, 2-4 items per thread
+  const long long max_blocks = (long long)num_sms() * 8 * 4;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool fast = (T == 8) && aligned16(phi) && aligned16(out) && (OP == OP_PHISUM || aligned16(a)) &&
+                    (add == nullptr || aligned16(add));
+  if (fast) {
+    const long long n_items = n_pix * 2;
+    long long blocks = (n_items + threads - 1) / threads;
+    if (blocks > max_blocks) blocks = max_blocks;
+    gap_t8_kernel<OP><<<(unsigned)blocks, threads, 0, st>>>(a, y, phi, phi_sum, add, out, n_items);
+  } else {
+    long long blocks = (n_pix + threads - 1) / threads;
+    if (blocks > max_blocks) blocks = max_blocks;
+    gap_generic_kernel<OP><<<(unsigned)blocks, threads, 0, st>>>(a, y, phi, phi_sum, add, out, n_pix, T);
+  }
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+int gap_step_launch(const float* z, const float* y, const float* phi, const float* phi_sum, float* out, int B,
+                    int H, int W, int T, void* stream) {
+  return launch_gap<OP_STEP>(z, y, phi, phi_sum, nullptr, out, B, H, W, T, stream);
+}
+
+}  // namespace deqsci
+
+using namespace deqsci;
+
+extern "C" int deqsci_gap_forward(const float* x, const float* phi, float* out, int B, int H, int W, int T,
+                                  void* stream) {
+  return launch_gap<OP_FORWARD>(x, nullptr, phi, nullptr, nullptr, out, B, H, W, T, stream);
+}
+extern "C" int deqsci_gap_adjoint(const float* y, const float* phi, float* out, int B, int H, int W, int T,
+                                  void* stream) {
+  return launch_gap<OP_ADJOINT>(y, nullptr, phi, nullptr, nullptr, out, B, H, W, T, stream);
+}
+extern "C" int deqsci_phi_sum(const float* phi, float* out, int B, int H, int W, int T, void* stream) {
+  return launch_gap<OP_PHISUM>(nullptr, nullptr, phi, nullptr, nullptr, out, B, H, W, T, stream);
+}
+extern "C" int deqsci_gap_step(const float* z, const float* y, const float* phi, const float* phi_sum, float* out,
+                               int B, int H, int W, int T, void* stream) {
+  return launch_gap<OP_STEP>(z, y, phi, phi_sum, nullptr, out, B, H, W, T, stream);
+}
+extern "C" int deqsci_gap_vjp(const float* v, const float* phi, const float* phi_sum, const float* add, float* out,
+                              int B, int H, int W, int T, void* stream) {
+  return launch_gap<OP_VJP>(v, nullptr, phi, phi_sum, add, out, B, H, W, T, stream);
+}

@@ -1,0 +1,153 @@
+"""Device-side denoiser plan: owns a deqsci_denoiser handle (packed / split weights on one GPU)
+and its scratch workspace.  Built by the nn.Module mirrors in deqsci_b200.networks from their
+current parameters."""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvLayer, DeqsciError, check, lib
+from .ops import _bcast_phi, _req, _stream
+
+
+def default_precision():
+    """DEQSCI_PRECISION in {tc_split (default, parity mode), fp32, tc_single}."""
+    name = os.environ.get("DEQSCI_PRECISION", "tc_split")
+    if name not in _lib.PRECISIONS:
+        raise DeqsciError("DEQSCI_PRECISION=%r not in %s" % (name, sorted(_lib.PRECISIONS)))
+    return name
+
+
+def _f32(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _destroy(handle):
+    try:
+        lib().deqsci_denoiser_destroy(handle)
+    except Exception:
+        pass
+
+
+class NativeDenoiser:
+    """kind: 'ffdnet' | 'dncnn'.  layers: list of dicts {weight [O,I,3,3], scale [O]|None,
+    bias [O]|None, relu bool} (host arrays).  Lives on `device`."""
+
+    def __init__(self, kind, layers, precision=None, device=None):
+        self.kind = kind
+        self.precision = precision or default_precision()
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise DeqsciError("NativeDenoiser needs a CUDA device (got %s): no CPU path" % self.device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        keep = []
+        arr = (ConvLayer * len(layers))()
+        for i, L in enumerate(layers):
+            w = _f32(L["weight"])
+            keep.append(w)
+            arr[i].cin, arr[i].cout, arr[i].relu = int(w.shape[1]), int(w.shape[0]), int(bool(L.get("relu", False)))
+            arr[i].weight_host = w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            for key, field in (("scale", "scale_host"), ("bias", "bias_host")):
+                v = L.get(key)
+                if v is not None:
+                    v = _f32(v)
+                    keep.append(v)
+                    setattr(arr[i], field, v.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_denoiser_create(_lib.NET_FFDNET if kind == "ffdnet" else _lib.NET_DNCNN,
+                                               _lib.PRECISIONS[self.precision], len(layers), arr,
+                                               ctypes.byref(handle)), "deqsci_denoiser_create")
+        self._h = handle
+        self._fin = weakref.finalize(self, _destroy, handle)
+        self._ws = None
+        self.num_layers = len(layers)
+
+    def _workspace(self, B, H, W, T):
+        need = lib().deqsci_denoiser_workspace_bytes(self._h, B, H, W, T)
+        if need == 0:
+            raise DeqsciError("unsupported cube shape B=%d H=%d W=%d T=%d: %s" % (
+                B, H, W, T, lib().deqsci_last_error().decode()))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check_dev(self, t):
+        if t.device != self.device:
+            raise DeqsciError("tensor on %s but denoiser plan lives on %s" % (t.device, self.device))
+
+    def denoise_residual(self, zin, sigma=0.0, out=None):
+        """out[B,H,W,T] = zin - D(zin), frames b*T+t, one sigma for the whole call."""
+        zin = _req(zin, "z", 4)
+        self._check_dev(zin)
+        B, H, W, T = (int(s) for s in zin.shape)
+        if out is None:
+            out = torch.empty_like(zin)
+        if zin.numel() == 0:
+            return out
+        ws = self._workspace(B, H, W, T)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_denoise_residual(self._h, zin.data_ptr(), float(sigma), out.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), B, H, W, T, _stream(zin)), "deqsci_denoise_residual")
+        return out
+
+    def iterate(self, z, y, phi, phi_sum, sigma=0.0, out=None):
+        """out = denoise_residual(gap_step(z, y, phi, phi_sum)): one call of the iterate map f."""
+        z, y = _req(z, "z", 4), _req(y, "y", 3)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
+        self._check_dev(z)
+        B, H, W, T = (int(s) for s in z.shape)
+        if tuple(phi.shape) != (B, H, W, T) or tuple(y.shape) != (B, H, W) or tuple(phi_sum.shape) != (B, H, W):
+            raise DeqsciError("iterate: inconsistent shapes z %s y %s Phi %s Phi_sum %s" % (
+                tuple(z.shape), tuple(y.shape), tuple(phi.shape), tuple(phi_sum.shape)))
+        if out is None:
+            out = torch.empty_like(z)
+        if z.numel() == 0:
+            return out
+        ws = self._workspace(B, H, W, T)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_iterate(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                       float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W, T,
+                                       _stream(z)), "deqsci_iterate")
+        return out
+
+    def debug_hidden_layer(self, layer, act_in, NF, Hc, Wc):
+        """Testing hook: act_in fp16 [2, NF, Hc, Wc, 64] (hi plane, lo plane) -> same shape."""
+        assert act_in.dtype == torch.float16 and act_in.is_contiguous() and act_in.shape == (2, NF, Hc, Wc, 64)
+        out = torch.empty_like(act_in)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_debug_hidden_layer(self._h, layer, act_in.data_ptr(), out.data_ptr(), NF, Hc, Wc,
+                                                  _stream(act_in)), "deqsci_debug_hidden_layer")
+        return out
+
+
+class NativePlanCache:
+    """Mixin for the nn.Module mirrors: builds / caches a NativeDenoiser per (device, precision)
+    and rebuilds it when any parameter or buffer changed (tensor version counters)."""
+
+    def _plan_layers(self):  # -> (kind, [layer dicts])
+        raise NotImplementedError
+
+    def _plan_signature(self):
+        return tuple((id(t), t._version, t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+
+    def native_plan(self, device, precision=None):
+        precision = precision or getattr(self, "precision", None) or default_precision()
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        cache = self.__dict__.setdefault("_native_cache", {})
+        key = (str(device), precision)
+        sig = self._plan_signature()
+        hit = cache.get(key)
+        if hit is None or hit[0] != sig:
+            kind, layers = self._plan_layers()
+            cache[key] = (sig, NativeDenoiser(kind, layers, precision, device))
+        return cache[key][1]

@@ -1,0 +1,57 @@
+"""DnCNN-style CNN — drop-in for the reference's networks/provable/model/SimpleCNN_models.py:6-61
+(`DnCNN(channels, num_of_layers, lip, no_bn, adaptive, tag)`), used by cnn.ckpt (lip=0, 4 layers,
+no BN) and rsn_cnn.ckpt (lip=1: spectrally normalised convs).  state_dict keys: `dncnn.N.weight`
+or `dncnn.N.{weight_orig,weight,weight_u}`.  At inference forward runs libdeqsci's conv stack."""
+import torch
+import torch.nn as nn
+
+from ...._lib import DeqsciError
+from ....native import NativePlanCache
+from ...ffdnet.models import sequential_to_plan_layers
+from .conv_sn_chen import conv_spectral_norm
+
+
+class DnCNN(nn.Module, NativePlanCache):
+    def __init__(self, channels, num_of_layers=17, lip=1.0, no_bn=False, adaptive=False, tag='denoiser'):
+        super().__init__()
+        self.tag = tag
+        self.channels = channels
+        features = 64
+        if lip > 0.0:
+            sigmas = [pow(lip, 1.0 / num_of_layers)] * num_of_layers
+        else:
+            sigmas = [0.0] * num_of_layers
+        if adaptive:
+            sigmas = [5.0, 2.0, 1.0, 0.681, 0.464, 0.316]
+            assert len(sigmas) == num_of_layers, "Length of SN list uncompatible with num of layers."
+
+        def conv_layer(cin, cout, sigma):
+            conv = nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
+            return conv_spectral_norm(conv, sigma=sigma) if sigma > 0.0 else conv
+
+        mods = [conv_layer(channels, features, sigmas[0]), nn.ReLU(inplace=True)]
+        for i in range(1, num_of_layers - 1):
+            mods.append(conv_layer(features, features, sigmas[i]))
+            if not no_bn:
+                mods.append(nn.BatchNorm2d(features))
+            mods.append(nn.ReLU(inplace=True))
+        mods.append(conv_layer(features, channels, sigmas[-1]))
+        self.dncnn = nn.Sequential(*mods)
+
+    def _plan_layers(self):
+        if self.channels != 1:
+            raise DeqsciError("the native DnCNN path covers single-channel frames (the SCI path)")
+        return "dncnn", sequential_to_plan_layers(self.dncnn)
+
+    def uses_native(self, x):
+        return x.is_cuda and self.channels == 1 and not (self.training and torch.is_grad_enabled())
+
+    def forward(self, x):
+        if self.uses_native(x):
+            N, C, H, W = x.shape
+            frames = x.detach().reshape(N, H, W, 1).contiguous()      # cube with T = 1
+            out = self.native_plan(x.device).denoise_residual(frames, 0.0)
+            return (frames - out).reshape(N, C, H, W)                 # network output (predicted noise)
+        if not x.is_cuda and not self.training:
+            raise DeqsciError("DnCNN inference on %s: deqsci_b200 has no CPU path" % x.device)
+        return self.dncnn(x)

@@ -1,0 +1,106 @@
+"""Iterate map of DE-GAP — drop-in for the reference's EquilibriumProxGradSCI
+(solvers/equilibrium_solvers_yaping.py:382-436):
+
+    z' = z + At((y - A z) / Phi_sum)          GAP data-consistency step
+    z+ = z' - D(z')                           learned denoiser predicts the noise
+
+At inference the whole map is ONE C-ABI call (deqsci_iterate): the GAP step is fused into the first
+conv kernel, the residual subtract and layout change into the last.  The sigma schedule of the
+'ffdnet' tag (reset to 60/255 when y.mean() changes, else x0.971 per call, :409-413) is kept on
+the host as an fp32 scalar, without the reference's per-call device sync."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .._lib import DeqsciError
+from ..utils import cg_utils
+
+_SIGMA0 = np.float32(60 / 255)
+_DECAY = np.float32(0.971)
+
+
+class EquilibriumProxGradSCI(nn.Module):
+    def __init__(self, A, At, nonlinear_operator, eta, minval=-1, maxval=1):
+        super().__init__()
+        self.A = A
+        self.At = At
+        self.nonlinear_op = nonlinear_operator
+        self.minval = minval          # stored, never applied — as in the reference (no clamp in forward)
+        self.maxval = maxval
+        self.eta = eta
+        self.y = 0                    # mean of the measurement the sigma schedule belongs to
+        self._sigma = _SIGMA0
+        self._y_key = None
+        self.n_sigma_frames = 8
+
+    # ---- sigma schedule (host side) ------------------------------------------------------------
+    @property
+    def noise_sigma(self):
+        """Per-frame sigma vector, like the reference's attribute (:394,410,413)."""
+        dev = next(self.nonlinear_op.parameters()).device
+        return torch.full((self.n_sigma_frames,), float(self._sigma), dtype=torch.float32, device=dev)
+
+    def _advance_sigma(self, y):
+        """Reference :409-413: `if self.y != y.mean(): reset else: sigma *= 0.971`.  The mean of a
+        tensor we have already seen (same storage, same version) is not recomputed, so a solver
+        loop costs one device sync per new measurement instead of one per call."""
+        key = (y.data_ptr(), y._version, tuple(y.shape), str(y.device))
+        if key != self._y_key:
+            mean = float(y.mean())
+            self._y_key = key
+            if self.y != mean:
+                self.y = mean
+                self._sigma = _SIGMA0
+                return self._sigma
+        self._sigma = np.float32(self._sigma * _DECAY)
+        return self._sigma
+
+    def skip_call(self):
+        """Advances the sigma schedule as one forward() call would, without computing anything
+        (DEQFixedPoint uses it for the reference's wasted second post-solver call at inference)."""
+        if self.nonlinear_op.tag == 'ffdnet':
+            self._sigma = np.float32(self._sigma * _DECAY)
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def _native_ok(self, z):
+        op = self.nonlinear_op
+        return (z.is_cuda and hasattr(op, "native_plan") and op.tag in ('ffdnet', 'denoiser')
+                and getattr(op, "uses_native", lambda t: False)(z))
+
+    def forward(self, z, y, Phi, Phi_sum, out=None):
+        bsz, w, h, c = z.shape
+        tag = self.nonlinear_op.tag
+        if self._native_ok(z):
+            sigma = 0.0
+            if tag == 'ffdnet':
+                self.n_sigma_frames = bsz * c
+                sigma = float(self._advance_sigma(y))
+            plan = self.nonlinear_op.native_plan(z.device)
+            if self.A is cg_utils.A_torch_ and self.At is cg_utils.At_torch_:
+                return plan.iterate(z, y, Phi, Phi_sum, sigma, out=out)
+            # custom operator callables: unfused data-consistency step, native denoiser
+            fb = self.A(z, Phi)
+            z = z + self.At((y - fb) / Phi_sum, Phi)
+            return plan.denoise_residual(z, sigma, out=out)
+        if not z.is_cuda and not (self.nonlinear_op.training and torch.is_grad_enabled()):
+            raise DeqsciError("EquilibriumProxGradSCI inference on %s: deqsci_b200 has no CPU path" % z.device)
+        return self._autograd_forward(z, y, Phi, Phi_sum)
+
+    def _autograd_forward(self, z, y, Phi, Phi_sum):
+        """Graph-attached evaluation for training (PyTorch autograd; not the inference hot path)."""
+        bsz, w, h, c = z.shape
+        tag = self.nonlinear_op.tag
+        fb = torch.sum(z * Phi, dim=3)
+        z = z + ((y - fb) / Phi_sum)[:, :, :, None] * Phi
+        frames = z.permute(0, 3, 1, 2).contiguous().view(bsz * c, 1, w, h)
+        if tag == 'ffdnet':
+            self.n_sigma_frames = bsz * c
+            sigma = float(self._advance_sigma(y))
+            noise = self.nonlinear_op(frames, torch.full((bsz * c,), sigma, dtype=z.dtype, device=z.device))
+            return z - noise.view(bsz, c, w, h).permute(0, 2, 3, 1)
+        if tag == 'denoiser':
+            noise = self.nonlinear_op(frames)
+            return z - noise.view(bsz, c, w, h).permute(0, 2, 3, 1)
+        if tag == 'conv2d':
+            return self.nonlinear_op(frames).view(bsz, c, w, h).permute(0, 2, 3, 1)
+        raise DeqsciError("nonlinear_op tag %r is not on the DE-GAP path built here" % (tag,))

@@ -1,0 +1,193 @@
+"""Fixed-point solvers and the DEQ wrapper — drop-in for the reference's
+solvers/new_equilibrium_utils_yaping.py (andersonexp :153-189, anderson :114-150,
+forward_iteration :213-222, DEQFixedPoint :241-281).
+
+Same signatures and return values.  The Anderson bookkeeping (residual history, Gram matrix,
+bordered (n+1)x(n+1) solve, mixing, residual norms) runs in libdeqsci's kernels (anderson.cu): the
+history is kept slot-major so every slot is a contiguous cube that the iterate map reads and writes
+in place, only the changed Gram row is recomputed, and the residual the reference fetches with two
+.item() calls per iteration comes back as one 16-byte async copy."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .._lib import DeqsciError, check, lib
+from ..ops import _req, _stream
+
+MAX_M = 8
+
+
+def _call_f(f, x, out):
+    """Calls the iterate map; maps that can write straight into a history slot advertise it."""
+    if getattr(f, "supports_out", False):
+        r = f(x, out=out)
+        if r is not out:
+            out.copy_(r)
+        return out
+    out.copy_(f(x).reshape(out.shape))
+    return out
+
+
+class _AndersonState:
+    """Device buffers of one solve: X, F, G [m,B,N] (slot-major), gram [B,m,m], alpha [B,m], res."""
+
+    def __init__(self, x0, m):
+        if not x0.is_cuda:
+            raise DeqsciError("Anderson solver on %s: deqsci_b200 has no CPU path" % x0.device)
+        if m < 1 or m > MAX_M:
+            raise DeqsciError("Anderson history m=%d unsupported (1..%d)" % (m, MAX_M))
+        self.B = int(x0.shape[0])
+        self.N = int(x0[0].numel())
+        self.m = m
+        self.shape = tuple(x0.shape)
+        dev = x0.device
+        hist = torch.zeros((3, m, self.B, self.N), dtype=torch.float32, device=dev)
+        self.X, self.F, self.G = hist[0], hist[1], hist[2]
+        self.gram = torch.zeros((self.B, m, m), dtype=torch.float32, device=dev)
+        self.alpha = torch.zeros((self.B, m), dtype=torch.float32, device=dev)
+        self.res_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.res_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.scratch = torch.empty(lib().deqsci_anderson_scratch_floats(self.B, m, self.N), dtype=torch.float32,
+                                   device=dev)
+        self.dev = dev
+
+    def slot(self, buf, s):
+        return buf[s].view(self.shape)
+
+    def update(self, slot, n, lam, eps):
+        with torch.cuda.device(self.dev):
+            check(lib().deqsci_anderson_update(self.X.data_ptr(), self.F.data_ptr(), self.G.data_ptr(),
+                                               self.gram.data_ptr(), self.alpha.data_ptr(), self.res_dev.data_ptr(),
+                                               self.scratch.data_ptr(), self.B, self.m, self.N, slot, n,
+                                               float(lam), float(eps), _stream(self.X)), "deqsci_anderson_update")
+
+    def mix(self, slot, n, beta):
+        with torch.cuda.device(self.dev):
+            check(lib().deqsci_anderson_mix(self.X.data_ptr(), self.F.data_ptr(), self.alpha.data_ptr(), self.B,
+                                            self.m, self.N, slot, n, float(beta), _stream(self.X)),
+                  "deqsci_anderson_mix")
+
+    def fetch_res(self, eps):
+        """(||F-X||, ||F||) of the last update -> the reference's python-float residual (:184)."""
+        self.res_host.copy_(self.res_dev, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return float(self.res_host[1]) / (eps + float(self.res_host[2]))
+
+
+def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
+    x0 = _req(x0, "x0")
+    st = _AndersonState(x0, m)
+    st.slot(st.X, 0).copy_(x0)
+    _call_f(f, st.slot(st.X, 0), st.slot(st.F, 0))
+    if m == 1:
+        raise DeqsciError("Anderson history m must be >= 2")
+    st.slot(st.X, 1).copy_(st.slot(st.F, 0))
+    _call_f(f, st.slot(st.X, 1), st.slot(st.F, 1))
+    st.update(0, 1, lam, eps)          # Gram entries of the two start-up slots
+    st.update(1, 2, lam, eps)          # ... and alpha for k = 2
+    res_list, res, current_k = [], None, 0
+    for k in range(2, max_iter):
+        current_k = k
+        n = min(k, m)
+        s = k % m
+        st.mix(s, n, beta)
+        _call_f(f, st.slot(st.X, s), st.slot(st.F, s))
+        # the same launch pair produces this iteration's residual and the next iteration's alpha
+        st.update(s, min(k + 1, m), lam, eps)
+        res = st.fetch_res(eps)
+        res_list.append(res)
+        if res < tol:
+            break
+    out = st.slot(st.X, current_k % m).clone()
+    return out, (res_list if keep_res else res)
+
+
+def andersonexp(f, x0, m=5, lam=1e-4, max_iter=50, tol=1e-5, beta=1.0):
+    """Anderson acceleration for x0 [B,H,W,T]; returns (X[k % m] view_as x0, float residual)."""
+    return _anderson_core(f, x0, m, lam, max_iter, tol, beta, 1e-5, keep_res=False)
+
+
+def anderson(f, x0, m=5, lam=1e-4, max_iter=50, tol=1e-2, beta=1.0):
+    """Same update for NCHW inputs; returns (x, [residual per iteration])."""
+    return _anderson_core(f, x0, m, lam, max_iter, tol, beta, 1e-5, keep_res=True)
+
+
+def forward_iteration(f, x0, max_iter=50, tol=1e-5):
+    """Picard iteration; returns (f0, [res]) with res = ||f0 - x|| / (1e-7 + ||f0||)."""
+    x0 = _req(x0, "x0")
+    dev = x0.device
+    f0 = f(x0)
+    res = []
+    scratch = torch.empty(lib().deqsci_anderson_scratch_floats(1, 1, x0.numel()), dtype=torch.float32, device=dev)
+    res_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+    res_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    for _ in range(max_iter):
+        x = f0
+        f0 = f(x)
+        a, b = _req(f0, "f(x)"), _req(x, "x")
+        with torch.cuda.device(dev):
+            check(lib().deqsci_residual(a.data_ptr(), b.data_ptr(), res_dev.data_ptr(), scratch.data_ptr(),
+                                        a.numel(), 1e-7, _stream(a)), "deqsci_residual")
+        res_host.copy_(res_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        res.append(float(res_host[1]) / (1e-7 + float(res_host[2])))
+        if res[-1] < tol:
+            break
+    return f0, res
+
+
+class _BoundIterate:
+    """f(z) = self.f(z, x, Phi, Phi_sum) with optional in-place output (history slots)."""
+
+    def __init__(self, f, x, Phi, Phi_sum):
+        self.f, self.x, self.Phi, self.Phi_sum = f, x, Phi, Phi_sum
+        self.supports_out = hasattr(f, "_native_ok")
+
+    def __call__(self, z, out=None):
+        if out is not None and self.supports_out and self.f._native_ok(z):
+            return self.f(z, self.x, self.Phi, self.Phi_sum, out=out)
+        return self.f(z, self.x, self.Phi, self.Phi_sum)
+
+
+class DEQFixedPoint(nn.Module):
+    """DEQFixedPoint(f, solver, **kwargs).forward(x=y, Phi, Phi_sum, initial_point, train_flag)
+    (reference :241-281).  Inference (denoiser in eval mode or grad disabled): solver under
+    no_grad, one more f call = the reconstruction; the reference's second post-solver call only
+    feeds the backward hook, so it is skipped and just advances the sigma schedule.  Training:
+    graph-attached f call plus the implicit-differentiation backward hook, as in the reference."""
+
+    def __init__(self, f, solver, **kwargs):
+        super().__init__()
+        self.f = f
+        self.solver = solver
+        self.kwargs = kwargs
+        self.forward_res = None
+        self.backward_res = None
+
+    def _inference(self):
+        op = getattr(self.f, "nonlinear_op", None)
+        return (not torch.is_grad_enabled()) or (op is not None and not op.training)
+
+    def forward(self, x, Phi, Phi_sum, initial_point=None, train_flag=True):
+        init_point = torch.zeros_like(Phi.expand(x.shape[0], *Phi.shape[1:])) if initial_point is None else initial_point
+        bound = _BoundIterate(self.f, x, Phi, Phi_sum)
+        with torch.no_grad():
+            z, self.forward_res = self.solver(bound, init_point, **self.kwargs)
+        if self._inference():
+            with torch.no_grad():
+                z = bound(z)
+            if hasattr(self.f, "skip_call"):
+                self.f.skip_call()
+            return z
+        z = self.f(z, x, Phi, Phi_sum)
+        z0 = z.clone().detach().requires_grad_()
+        f0 = self.f(z0, x, Phi, Phi_sum)
+
+        def backward_hook(grad):
+            g, self.backward_res = self.solver(
+                lambda v: torch.autograd.grad(f0, z0, v, retain_graph=True)[0] + grad, grad, **self.kwargs)
+            return g
+
+        z.register_hook(backward_hook)
+        return z

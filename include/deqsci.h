@@ -1,0 +1,170 @@
+/*
+ * deqsci.h — C-ABI of libdeqsci (sm_100a): the DE-GAP reconstruction hot path of
+ * IndigoPurple/DEQSCI, hand-written CUDA behind plain pointers.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); each entry point below
+ * replaces the PyTorch call sites named in its comment (paths relative to the reference root).
+ * The Python host mirror of the reference interface (deqsci_b200/) binds these with ctypes; the
+ * stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *  - tensors are fp32, contiguous, in the reference's own layouts:
+ *        cube  z, Phi : [B, H, W, T]   (T innermost)        snapshot y, Phi_sum : [B, H, W]
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - functions never allocate or free caller memory, never synchronise the stream (except
+ *    deqsci_denoiser_create, which uploads weights synchronously) and return 0 on success or a
+ *    negative deqsci_status; deqsci_last_error() gives the text for the calling thread;
+ *  - handles are immutable after creation, so calls are re-entrant per (handle, stream) as long
+ *    as each concurrent call has its own workspace.
+ */
+#ifndef DEQSCI_H_
+#define DEQSCI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEQSCI_VERSION 100
+
+typedef enum {
+  DEQSCI_OK = 0,
+  DEQSCI_ERR_INVALID = -1,   /* bad argument (null pointer, unsupported shape, ...)            */
+  DEQSCI_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed                             */
+  DEQSCI_ERR_WORKSPACE = -3, /* workspace too small                                             */
+  DEQSCI_ERR_ARCH = -4       /* device is not sm_100 (tcgen05 path unavailable)                 */
+} deqsci_status;
+
+int deqsci_version(void);
+const char* deqsci_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) SCI operator / GAP data-consistency step — one fused, vectorised, memory-bound kernel each.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out[B,H,W] = sum_t x*Phi.            Replaces A_torch_, utils/cg_utils.py:85-90. */
+int deqsci_gap_forward(const float* x, const float* phi, float* out,
+                       int B, int H, int W, int T, void* stream);
+
+/* out[B,H,W,T] = y[...,None]*Phi.      Replaces At_torch_ / initial_point, utils/cg_utils.py:124-129,228-229. */
+int deqsci_gap_adjoint(const float* y, const float* phi, float* out,
+                       int B, int H, int W, int T, void* stream);
+
+/* out[B,H,W] = sum_t Phi, zeros -> 1.  Replaces training/sci_equilibrium_training.py:61-62,162-163. */
+int deqsci_phi_sum(const float* phi, float* out, int B, int H, int W, int T, void* stream);
+
+/* out = z + Phi * ((y - sum_t z*Phi) / phi_sum)[...,None].
+ * Replaces solvers/equilibrium_solvers_yaping.py:399-400 (A, subtract, divide, At, add: 6 launches). */
+int deqsci_gap_step(const float* z, const float* y, const float* phi, const float* phi_sum,
+                    float* out, int B, int H, int W, int T, void* stream);
+
+/* out = v - Phi * ((sum_t v*Phi) / phi_sum)[...,None]  (+ add[B,H,W,T] if add != NULL).
+ * Vector-Jacobian product of deqsci_gap_step w.r.t. z; for tag 'ffdnet' it is the whole VJP of the
+ * iterate map (the denoiser input is detached, networks/ffdnet/models.py:103-104), used by the
+ * backward solve at solvers/new_equilibrium_utils_yaping.py:274-277. */
+int deqsci_gap_vjp(const float* v, const float* phi, const float* phi_sum, const float* add,
+                   float* out, int B, int H, int W, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Learned denoiser: 3x3 conv stack (pad 1, stride 1, no conv bias), 64 hidden features.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct deqsci_denoiser deqsci_denoiser; /* opaque */
+
+typedef enum {
+  DEQSCI_NET_FFDNET = 0, /* networks/ffdnet/models.py:70-108: pixel-unshuffle + noise map (5 ch) ->
+                            convs at H/2 x W/2 -> 4 ch -> pixel-shuffle                              */
+  DEQSCI_NET_DNCNN = 1   /* networks/provable/model/SimpleCNN_models.py:6-61: 1 ch -> convs -> 1 ch  */
+} deqsci_net_kind;
+
+typedef enum {
+  DEQSCI_PREC_TC_SPLIT = 0, /* hidden 64->64 layers on tcgen05 tensor cores, fp16 hi/lo operand
+                               split (3 MMA products, fp32 TMEM accumulation) — the parity mode     */
+  DEQSCI_PREC_FP32 = 1,     /* hidden layers on CUDA cores in fp32 (slow; validation)               */
+  DEQSCI_PREC_TC_SINGLE = 2 /* single fp16 MMA pass (fast, NOT parity: reported as such)            */
+} deqsci_precision;
+
+/* One conv layer: weight_host [cout,cin,3,3] fp32 (PyTorch OIHW); optional per-output-channel
+ * affine applied after the conv (folded eval-mode BatchNorm, networks/ffdnet/models.py:58):
+ * out = conv*scale + bias; then ReLU if relu != 0. scale_host/bias_host may be NULL (= 1 / 0). */
+typedef struct {
+  int cin, cout, relu;
+  const float* weight_host;
+  const float* scale_host;
+  const float* bias_host;
+} deqsci_conv_layer;
+
+/* Builds the device-side plan (packs / splits weights). layers[0].cin must be 5 (FFDNET) or 1
+ * (DNCNN), hidden layers 64->64, last layer cout 4 (FFDNET) or 1 (DNCNN).  Synchronous. */
+int deqsci_denoiser_create(int net_kind, int precision, int num_layers,
+                           const deqsci_conv_layer* layers_host, deqsci_denoiser** out);
+int deqsci_denoiser_destroy(deqsci_denoiser* h);
+
+/* Bytes of scratch (activation ping-pong planes) for a [B,H,W,T] cube. */
+size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
+
+/* out[B,H,W,T] = zin - D(zin) where D runs on the B*T frames zin[b,:,:,t] (frame index b*T+t) and,
+ * for FFDNET, the constant noise map sigma (same for every frame of the call).
+ * Replaces the permute/view + net(...) + `z - noise.view().permute()` of
+ * solvers/equilibrium_solvers_yaping.py:415-420 and everything under networks/ffdnet/models.py:98-108.
+ * `out` may alias `zin`. */
+int deqsci_denoise_residual(const deqsci_denoiser* h, const float* zin, float sigma, float* out,
+                            void* workspace, size_t workspace_bytes,
+                            int B, int H, int W, int T, void* stream);
+
+/* The whole iterate map f(z) = denoise_residual(gap_step(z)):
+ * EquilibriumProxGradSCI.forward, solvers/equilibrium_solvers_yaping.py:396-436.
+ * `out` may alias `z`. */
+int deqsci_iterate(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                   const float* phi_sum, float sigma, float* out,
+                   void* workspace, size_t workspace_bytes,
+                   int B, int H, int W, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Anderson acceleration state update (andersonexp / anderson,
+ *     solvers/new_equilibrium_utils_yaping.py:114-189).  History X, F, G : [m, B, N] fp32 — slot-major,
+ *     so that slot s is a contiguous [B,H,W,T] cube the iterate map reads / writes in place (the
+ *     reference's [B,m,N] buffer is private to andersonexp, :159-160).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Number of floats of `scratch` needed by deqsci_anderson_update. */
+size_t deqsci_anderson_scratch_floats(int B, int m, long long N);
+
+/* After F[slot] = f(X[slot]) has been written, with n valid slots (0..n-1, slot < n):
+ *   G[slot]     = F[slot] - X[slot]                                     (:177)
+ *   gram[b,slot,j] = gram[b,j,slot] = <G[slot,b], G[j,b]>  for j < n     (:178, incremental row)
+ *   alpha[b,0:n] = solution[1:n+1] of the bordered system [[0,1^T],[1,GG^T+lam I]] a = e0   (:168-171,180)
+ *                  (LU with partial pivoting, fp32, one lane per sample)
+ *   res[0] = ||G[slot]|| / (res_eps + ||F[slot]||) over the whole batch  (:184);  res[1], res[2] = the two norms
+ * gram [B,m,m], alpha [B,m], res [4] are device buffers owned by the caller.  Two launches. */
+int deqsci_anderson_update(const float* X, const float* F, float* G, float* gram, float* alpha,
+                           float* res, float* scratch, int B, int m, long long N, int slot, int n,
+                           float lam, float res_eps, void* stream);
+
+/* X[slot,b] = beta * sum_{j<n} alpha[b,j] F[j,b] + (1-beta) * sum_{j<n} alpha[b,j] X[j,b]   (:182).
+ * When beta == 1 the X term is not read (0*X dropped: differs from the reference only if X holds
+ * NaN/Inf). */
+int deqsci_anderson_mix(float* X, const float* F, const float* alpha, int B, int m, long long N,
+                        int slot, int n, float beta, void* stream);
+
+/* res[0] = ||a-b|| / (res_eps + ||a||), res[1] = ||a-b||, res[2] = ||a|| over all `count` floats
+ * (forward_iteration, solvers/new_equilibrium_utils_yaping.py:219).  scratch as above (B=1,N=count). */
+int deqsci_residual(const float* a, const float* b, float* res, float* scratch, long long count,
+                    float res_eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Testing hook: runs ONE hidden 64->64 layer (index `layer`, 0 < layer < num_layers-1) of a plan on
+ * caller-provided activation planes: channels-last [NF,Hc,Wc,64], fp16 hi plane followed by the
+ * fp16 lo plane (value = hi + lo*2^-11).  Used by tests/ to compare the tcgen05 kernel against the
+ * fp32 CUDA-core kernel layer by layer.
+ * ---------------------------------------------------------------------------------------------- */
+int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* act_in, void* act_out,
+                              int NF, int Hc, int Wc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEQSCI_H_ */

@@ -1,0 +1,338 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C-ABI, against the numpy oracle on the
+same seeded inputs and against the golden vectors produced by the reference's own code.
+
+Bars (BASELINE.json north_star): operator <= 1e-6 relative; per-iterate relative L2 <= 1e-3;
+final PSNR within 0.05 dB, SSIM within 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_scene, load_weights, rel_l2
+from oracle import deqsci_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DENOISERS = ["ffdnet", "SimpleCNN", "RealSN_SimpleCNN"]
+TAG = {"ffdnet": "ffdnet", "SimpleCNN": "denoiser", "RealSN_SimpleCNN": "denoiser"}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from deqsci_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "libdeqsci.so missing: the CUDA path must be built"
+    _lib.lib()
+    return torch.device("cuda", 0)
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def build_solver(d, dev, precision=None):
+    from deqsci_b200.networks.ffdnet.models import FFDNet
+    from deqsci_b200.networks.provable.model.SimpleCNN_models import DnCNN
+    from deqsci_b200.solvers.equilibrium_solvers_yaping import EquilibriumProxGradSCI
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_
+    if d == "ffdnet":
+        net = FFDNet(num_input_channels=1, tag="ffdnet")
+    else:
+        net = DnCNN(1, num_of_layers=4, lip=1.0 if d == "RealSN_SimpleCNN" else 0.0, no_bn=True, tag="denoiser")
+    if precision:
+        net.precision = precision
+    net.eval()
+    solver = EquilibriumProxGradSCI(A=A_torch_, At=At_torch_, nonlinear_operator=net, eta=0.2)
+    sd = {k: torch.from_numpy(v) for k, v in load_weights(d).items()}
+    solver.load_state_dict(sd, strict=False)
+    return solver.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) operator / GAP kernels
+# ---------------------------------------------------------------------------------------------
+def test_operator_golden(dev, small_vectors):
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_, initial_point, Phi_sum_
+    v = small_vectors
+    x, Phi = t(v["op_x"], dev), t(v["op_Phi"], dev)
+    y = A_torch_(x, Phi)
+    assert rel_l2(y.cpu().numpy(), v["op_A"]) <= 1e-6
+    assert np.abs(y.cpu().numpy() - v["op_A"]).max() <= 1e-6 * np.abs(v["op_A"]).max()
+    np.testing.assert_array_equal(At_torch_(t(v["op_A"], dev), Phi).cpu().numpy(), v["op_At"])
+    np.testing.assert_array_equal(initial_point(t(v["op_A"], dev), Phi, None, None).cpu().numpy(), v["op_x0"])
+    np.testing.assert_allclose(Phi_sum_(Phi).cpu().numpy(), v["op_Phi_sum"], rtol=1e-6)
+    np.testing.assert_array_equal(Phi_sum_(Phi[:1]).cpu().numpy(), v["op_Phi_sum"][:1])
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256, 8), (3, 17, 23, 8), (2, 16, 16, 5), (1, 1, 1, 8), (2, 9, 7, 1)])
+def test_gap_kernels_vs_oracle(dev, shape):
+    from deqsci_b200 import ops
+    rng = np.random.default_rng(sum(shape))
+    z = rng.standard_normal(shape).astype(np.float32)
+    Phi = (rng.random(shape) < 0.5).astype(np.float32)
+    if shape[0] > 1:
+        Phi[-1] = rng.random(shape[1:]).astype(np.float32)       # a grey mask
+    Phi[0, 0, 0] = 0                                             # a pixel no frame sees
+    y = rng.random(shape[:3]).astype(np.float32) * shape[3]
+    Ps = orc.phi_sum(Phi)
+    zt, Pt, yt, Pst = t(z, dev), t(Phi, dev), t(y, dev), t(Ps, dev)
+    tol = 1e-6
+    assert rel_l2(ops.gap_forward(zt, Pt).cpu().numpy(), orc.A(z, Phi)) <= tol
+    np.testing.assert_array_equal(ops.gap_adjoint(yt, Pt).cpu().numpy(), orc.At(y, Phi))
+    np.testing.assert_allclose(ops.phi_sum(Pt).cpu().numpy(), Ps, rtol=1e-6)
+    assert rel_l2(ops.gap_step(zt, yt, Pt, Pst).cpu().numpy(), orc.gap_step(z, y, Phi, Ps)) <= tol
+    assert rel_l2(ops.gap_vjp(zt, Pt, Pst).cpu().numpy(), orc.gap_vjp(z, Phi, Ps)) <= tol
+    add = rng.standard_normal(shape).astype(np.float32)
+    assert rel_l2(ops.gap_vjp(zt, Pt, Pst, add=t(add, dev)).cpu().numpy(), orc.gap_vjp(z, Phi, Ps) + add) <= tol
+
+
+def test_gap_adjointness_and_projector(dev):
+    """<A x, y> = <x, At y>; the GAP step is idempotent on the data (A(step(z)) = y where sum Phi > 0)
+    and linear in (z, y); the VJP is a projector: vjp(vjp(v)) = vjp(v) for a binary mask."""
+    from deqsci_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shape = (2, 64, 48, 8)
+    x = torch.rand(shape, generator=g).to(dev)
+    Phi = (torch.rand(shape, generator=g) < 0.5).float().to(dev)
+    y = torch.rand(shape[:3], generator=g).to(dev)
+    lhs = (ops.gap_forward(x, Phi).double() * y.double()).sum()
+    rhs = (x.double() * ops.gap_adjoint(y, Phi).double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * abs(float(rhs))
+    Ps = ops.phi_sum(Phi)
+    z1 = ops.gap_step(x, y * 4, Phi, Ps)
+    seen = Phi.sum(3) > 0
+    assert float((ops.gap_forward(z1, Phi) - y * 4)[seen].abs().max()) <= 2e-5
+    v1 = ops.gap_vjp(x, Phi, Ps)
+    assert rel_l2(ops.gap_vjp(v1, Phi, Ps).cpu().numpy(), v1.cpu().numpy()) <= 2e-6
+    assert ops.gap_forward(torch.empty(0, 4, 4, 8, device=dev), torch.empty(0, 4, 4, 8, device=dev)).shape == (0, 4, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) conv stack
+# ---------------------------------------------------------------------------------------------
+def _split_planes(x):
+    """fp32 [NF,H,W,64] -> fp16 [2,NF,H,W,64] (hi, lo*2^11)."""
+    hi = x.half()
+    lo = ((x - hi.float()) * 2048.0).half()
+    return torch.stack([hi, lo]).contiguous()
+
+
+def _join_planes(p):
+    return p[0].float() + p[1].float() / 2048.0
+
+
+@pytest.mark.parametrize("NF,Hc,Wc", [(2, 16, 16), (3, 9, 24), (1, 5, 130), (8, 128, 128), (2, 64, 256)])
+@pytest.mark.parametrize("precision", ["tc_split", "fp32"])
+def test_hidden_layer_vs_fp64_conv(dev, NF, Hc, Wc, precision):
+    """One 64->64 layer (tcgen05 split-fp16 kernel and the fp32 CUDA-core kernel) against
+    torch conv2d in fp64 on the same (hi+lo) inputs; affine + ReLU epilogue included."""
+    from deqsci_b200.native import NativeDenoiser
+    g = torch.Generator(device="cpu").manual_seed(NF * 1000 + Hc * 10 + Wc)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.06
+    scale = torch.rand(64, generator=g) * 2 + 0.1
+    bias = torch.randn(64, generator=g) * 0.3
+    layers = [{"weight": torch.randn(64, 1, 3, 3, generator=g), "relu": True},
+              {"weight": w, "scale": scale, "bias": bias, "relu": True},
+              {"weight": torch.randn(1, 64, 3, 3, generator=g), "relu": False}]
+    plan = NativeDenoiser("dncnn", layers, precision=precision, device=dev)
+    x = (torch.randn(NF, Hc, Wc, 64, generator=g) * 2).to(dev)
+    planes = _split_planes(x)
+    out = _join_planes(plan.debug_hidden_layer(1, planes, NF, Hc, Wc))
+    xin = _join_planes(planes).double().permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xin, w.double().to(dev), padding=1)
+    ref = torch.relu(ref * scale.double().to(dev).view(1, -1, 1, 1) + bias.double().to(dev).view(1, -1, 1, 1))
+    ref = ref.permute(0, 2, 3, 1)
+    err = float((out.double() - ref).norm() / ref.norm())
+    assert err <= 2e-6, err          # ~22-bit operands, fp32 accumulate
+    assert float((out.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("d", DENOISERS)
+@pytest.mark.parametrize("precision", ["tc_split", "fp32"])
+def test_denoiser_vs_oracle(dev, small_vectors, d, precision):
+    """denoise_residual (whole stack) on a 64x64x8 crop, B=2, vs the numpy oracle network."""
+    solver = build_solver(d, dev, precision)
+    rng = np.random.default_rng(3)
+    z = (small_vectors["crop_gt"] + 0.1 * rng.standard_normal(small_vectors["crop_gt"].shape)).astype(np.float32)
+    B, H, W, T = z.shape
+    sigma = np.float32(0.2)
+    sd = {k[len("nonlinear_op."):]: v for k, v in load_weights(d).items()}
+    frames = np.ascontiguousarray(z.transpose(0, 3, 1, 2)).reshape(B * T, 1, H, W)
+    if d == "ffdnet":
+        noise = orc.ffdnet_forward(frames, np.full(B * T, sigma, np.float32), sd)
+    else:
+        noise = orc.dncnn_forward(frames, sd)
+    want = z - noise.reshape(B, T, H, W).transpose(0, 2, 3, 1)
+    plan = solver.nonlinear_op.native_plan(dev)
+    got = plan.denoise_residual(t(z, dev), float(sigma)).cpu().numpy()
+    assert rel_l2(got, want) <= 2e-5
+    # module-level API of the reference: net(x[N,1,H,W], sigma[N]) -> predicted noise
+    xin = t(frames, dev)
+    if d == "ffdnet":
+        pred = solver.nonlinear_op(xin, torch.full((B * T,), float(sigma), device=dev))
+    else:
+        pred = solver.nonlinear_op(xin)
+    assert rel_l2(pred.cpu().numpy(), noise) <= 1e-4
+
+
+@pytest.mark.parametrize("d", DENOISERS)
+def test_f_two_calls_golden(dev, small_vectors, d):
+    """EquilibriumProxGradSCI.forward twice (sigma decays once) vs the reference's own outputs."""
+    v = small_vectors
+    solver = build_solver(d, dev)
+    Phi, y = t(v["crop_Phi"], dev), t(v["crop_y"], dev)
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    f1 = solver(x0, y, Phi, Ps)
+    f2 = solver(f1, y, Phi, Ps)
+    assert rel_l2(f1.cpu().numpy(), v["f1_" + d]) <= 2e-5
+    assert rel_l2(f2.cpu().numpy(), v["f2_" + d]) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) Anderson kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,m", [(1, 4096 * 3, 5), (3, 1000, 5), (2, 8 * 64 * 64, 3), (4, 37, 6)])
+def test_anderson_kernels_vs_numpy(dev, B, N, m):
+    """Ramp-up (n = 1..m) and wrap-around of the slot ring: gram rows, alpha, residual, mix."""
+    from deqsci_b200.solvers.new_equilibrium_utils_yaping import _AndersonState
+    rng = np.random.default_rng(B * 100 + m)
+    x0 = torch.zeros(B, N, device=dev)
+    st = _AndersonState(x0, m)
+    Xh = np.zeros((m, B, N), np.float32)
+    Fh = np.zeros((m, B, N), np.float32)
+    lam, eps = 1e-2, 1e-5
+    for step in range(2 * m + 1):
+        slot, n = step % m, min(step + 1, m)
+        Xh[slot] = rng.standard_normal((B, N)).astype(np.float32)
+        Fh[slot] = Xh[slot] + 0.3 * rng.standard_normal((B, N)).astype(np.float32)
+        st.X[slot].copy_(t(Xh[slot], dev))
+        st.F[slot].copy_(t(Fh[slot], dev))
+        st.update(slot, n, lam, eps)
+        res = st.fetch_res(eps)
+        G = (Fh[:n] - Xh[:n]).transpose(1, 0, 2)                       # [B,n,N]
+        alpha = orc.anderson_alpha(G, lam)
+        np.testing.assert_allclose(st.alpha.cpu().numpy()[:, :n], alpha, rtol=2e-4, atol=2e-6)
+        gram = np.matmul(G.astype(np.float64), G.astype(np.float64).transpose(0, 2, 1))
+        np.testing.assert_allclose(st.gram.cpu().numpy()[:, :n, :n], gram, rtol=2e-6, atol=1e-6)
+        want_res = np.linalg.norm(G[:, slot].astype(np.float64)) / (eps + np.linalg.norm(Fh[slot].astype(np.float64)))
+        assert abs(res - want_res) <= 2e-6 * want_res
+        for beta in (1.0, 0.7):
+            nxt = (step + 1) % m
+            keep = st.X[nxt].clone()
+            st.mix(nxt, n, beta)
+            a64 = st.alpha.cpu().numpy()[:, :n].astype(np.float64)
+            want = beta * np.einsum("bj,jbn->bn", a64, Fh[:n].astype(np.float64)) + \
+                (1 - beta) * np.einsum("bj,jbn->bn", a64, Xh[:n].astype(np.float64))
+            assert rel_l2(st.X[nxt].cpu().numpy(), want) <= 2e-6
+            st.X[nxt].copy_(keep)
+
+
+def test_residual_kernel(dev):
+    from deqsci_b200.solvers.new_equilibrium_utils_yaping import forward_iteration
+    a = torch.randn(3, 16, 16, 8, device=dev)
+    z, res = forward_iteration(lambda x: 0.5 * x + 1.0, a, max_iter=4, tol=0.0)
+    x = a * 0.5 + 1.0
+    want = []
+    for _ in range(4):
+        f0 = 0.5 * x + 1.0
+        want.append(float((f0 - x).double().norm()) / (1e-7 + float(f0.double().norm())))
+        x = f0
+    np.testing.assert_allclose(res, want, rtol=1e-5)
+    assert rel_l2(z.cpu().numpy(), x.cpu().numpy()) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# (4) solvers end to end on the golden crops (B = 2, 30 iterations, all three denoisers)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", DENOISERS)
+def test_deq_andersonexp_golden(dev, small_vectors, d):
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    solver = build_solver(d, dev)
+    Phi, y = t(v["crop_Phi"], dev), t(v["crop_y"], dev)
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    seen = []
+    h = solver.register_forward_pre_hook(lambda mod, args: seen.append(args[0].detach().clone()))
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=30, tol=1e-5)
+    z = deq.forward(y, Phi, Ps, initial_point=x0, train_flag=False)
+    h.remove()
+    assert len(seen) == 31                      # 30 solver calls + the reconstruction call
+    norms = np.array([float(s.double().norm()) for s in seen])
+    np.testing.assert_allclose(norms, v["deq30_innorm_" + d][:31], rtol=1e-4)
+    assert rel_l2(seen[10].cpu().numpy(), v["deq30_in10_" + d]) <= 1e-3      # per-iterate bar
+    assert rel_l2(z.cpu().numpy(), v["deq30_z_" + d]) <= 1e-3
+    assert abs(deq.forward_res - float(v["deq30_res_" + d])) <= 1e-2 * float(v["deq30_res_" + d])
+    # sigma schedule advanced exactly like the reference's 32 calls
+    if d == "ffdnet":
+        s = np.float32(60 / 255)
+        for _ in range(31):
+            s = np.float32(s * np.float32(0.971))
+        assert float(solver._sigma) == float(s)
+
+
+@pytest.mark.parametrize("d", DENOISERS)
+def test_forward_iteration_golden(dev, small_vectors, d):
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    solver = build_solver(d, dev)
+    Phi, y = t(v["crop_Phi"][:1], dev), t(v["crop_y"][:1], dev)
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    z, res = eq.forward_iteration(lambda q: solver(q, y, Phi, Ps), x0, max_iter=6, tol=1e-5)
+    assert rel_l2(z.cpu().numpy(), v["picard6_z_" + d]) <= 1e-4
+    np.testing.assert_allclose(res, v["picard6_res_" + d], rtol=1e-3)
+
+
+def test_per_iterate_trace_vs_oracle(dev, small_vectors):
+    """Every iterate of a 12-iteration Anderson run vs the numpy oracle (SimpleCNN weights)."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    d = "SimpleCNN"
+    Phi_n, y_n = v["crop_Phi"][:1], v["crop_y"][:1]
+    f_o = orc.ProxGradSCI(TAG[d], load_weights(d))
+    want = []
+    orc.andersonexp(lambda z: f_o(z, y_n, Phi_n, orc.phi_sum(Phi_n)), orc.At(y_n, Phi_n), m=5, lam=1e-2,
+                    max_iter=12, tol=1e-5, beta=1.0, trace=want)
+    solver = build_solver(d, dev)
+    Phi, y = t(Phi_n, dev), t(y_n, dev)
+    Ps = Phi_sum_(Phi)
+    got = []
+    h = solver.register_forward_pre_hook(lambda mod, args: got.append(args[0].detach().clone()))
+    eq.andersonexp(lambda q, out=None: solver(q, y, Phi, Ps), At_torch_(y, Phi), m=5, lam=1e-2, max_iter=12,
+                   tol=1e-5, beta=1.0)
+    h.remove()
+    got = got[2:]                                 # first two calls are x0 and f(x0)
+    assert len(got) == len(want) == 10
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert rel_l2(a.cpu().numpy(), b) <= 1e-3, k
+
+
+# ---------------------------------------------------------------------------------------------
+# (5) full-size reconstructions: PSNR / SSIM against the reference's numbers
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,scene", [("SimpleCNN", "drop8"), ("RealSN_SimpleCNN", "runner8"), ("ffdnet", "drop8")])
+def test_full_scene_psnr_vs_reference(dev, full_recon, d, scene):
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    key = "%s_%s_0" % (d, scene)
+    if key + "_psnr" not in full_recon:
+        pytest.skip("no reference reconstruction recorded for " + key)
+    gt, mask, meas = load_scene(scene)
+    solver = build_solver(d, dev)
+    Phi, y = t(mask[None], dev), t(meas[None, :, :, 0], dev)
+    Ps = Phi_sum_(Phi)
+    max_iter = 180 if d == "ffdnet" else 100
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=max_iter, tol=1e-5)
+    z = deq.forward(y, Phi, Ps, initial_point=At_torch_(y, Phi), train_flag=False)
+    rec = z.clip(0, 1).cpu().numpy()
+    g = gt[None, :, :, 0:8]
+    psnr = orc.psnr(g, rec)
+    ssim = orc.ssim(rec.transpose(0, 3, 1, 2), g.transpose(0, 3, 1, 2))
+    assert abs(psnr - float(full_recon[key + "_psnr"])) <= 0.05, (psnr, float(full_recon[key + "_psnr"]))
+    assert abs(ssim - float(full_recon[key + "_ssim"])) <= 1e-3
+    crop = z[0, 96:160, 96:160].cpu().numpy()
+    assert rel_l2(crop, full_recon[key + "_z_crop"]) <= 1e-3

@@ -1,0 +1,125 @@
+"""CPU: the C-ABI library loads and exports every symbol include/deqsci.h declares; host-side
+logic (checkpoint key compatibility, sigma schedule, loud failure without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_weights
+
+import deqsci_b200
+from deqsci_b200 import _lib
+from deqsci_b200.networks.ffdnet.models import FFDNet, sequential_to_plan_layers
+from deqsci_b200.networks.provable.model.SimpleCNN_models import DnCNN
+from deqsci_b200.solvers.equilibrium_solvers_yaping import EquilibriumProxGradSCI
+from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq_utils
+from deqsci_b200.utils.cg_utils import A_torch_, At_torch_
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "deqsci.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(deqsci_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deqsci_b200.build import build_library
+    build_library()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib.SIGNATURES) == names           # the ctypes table binds exactly the header
+    assert _lib.lib().deqsci_version() == 100
+
+
+def test_no_cpu_fallback():
+    x = torch.rand(1, 8, 8, 8)
+    with pytest.raises(deqsci_b200.DeqsciError):
+        A_torch_(x, x)
+    with pytest.raises(deqsci_b200.DeqsciError):
+        At_torch_(x[..., 0], x)
+    net = FFDNet(1, "ffdnet").eval()
+    with pytest.raises(deqsci_b200.DeqsciError):
+        net(torch.rand(2, 1, 8, 8), torch.full((2,), 0.1))
+    f = EquilibriumProxGradSCI(A_torch_, At_torch_, net, 0.2)
+    with pytest.raises(deqsci_b200.DeqsciError):
+        f(x, x[..., 0], x, x[..., 0])
+    with pytest.raises(deqsci_b200.DeqsciError):
+        eq_utils.andersonexp(lambda z: z, x)
+
+
+def _build(denoiser):
+    if denoiser == "ffdnet":
+        return FFDNet(num_input_channels=1, tag="ffdnet")
+    return DnCNN(1, num_of_layers=4, lip=1.0 if denoiser == "RealSN_SimpleCNN" else 0.0, no_bn=True, tag="denoiser")
+
+
+@pytest.mark.parametrize("d", ["ffdnet", "SimpleCNN", "RealSN_SimpleCNN"])
+def test_reference_checkpoints_load_strict(d):
+    """video_sci_proxgrad.py:223 does solver.load_state_dict(strict) with keys 'nonlinear_op.*'."""
+    sd = {k: torch.from_numpy(v) for k, v in load_weights(d).items()}
+    if d == "RealSN_SimpleCNN":     # weight_u probes are not shipped in the fixture; shapes are
+        g = np.load(os.path.join(ROOT, "tests/golden/weights_rsn_cnn.npz"))
+        for k in g.files:
+            if k.startswith("shape::"):
+                sd[k[len("shape::"):]] = torch.zeros(*g[k].tolist())
+    solver = EquilibriumProxGradSCI(A_torch_, At_torch_, _build(d), 0.2)
+    if d == "ffdnet":               # net_gray.pth has no num_batches_tracked entries (BatchNorm tolerates it)
+        missing, unexpected = solver.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing)
+        assert len(solver.state_dict()) == 80
+    else:
+        solver.load_state_dict(sd, strict=True)
+    n_params = sum(p.numel() for p in solver.parameters())
+    assert n_params == {"ffdnet": 486080, "SimpleCNN": 74880, "RealSN_SimpleCNN": 74880}[d]
+
+
+def test_plan_layers_fold_batchnorm():
+    net = FFDNet(1, "ffdnet").eval()
+    sd = {k[len("nonlinear_op."):]: torch.from_numpy(v) for k, v in load_weights("ffdnet").items()}
+    net.load_state_dict(sd, strict=False)
+    layers = sequential_to_plan_layers(net.intermediate_dncnn.itermediate_dncnn)
+    assert len(layers) == 15
+    assert [tuple(l["weight"].shape[:2]) for l in layers] == [(64, 5)] + [(64, 64)] * 13 + [(4, 64)]
+    assert [l["relu"] for l in layers] == [True] * 14 + [False]
+    assert layers[0]["scale"] is None and layers[14]["scale"] is None
+    bn = net.intermediate_dncnn.itermediate_dncnn[3]
+    x = torch.randn(64, dtype=torch.float64)
+    want = (x - bn.running_mean.double()) / torch.sqrt(bn.running_var.double() + bn.eps) * bn.weight.double() + bn.bias.double()
+    got = x * layers[1]["scale"].double() + layers[1]["bias"].double()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_sigma_schedule_host_side():
+    """60/255, then fp32 multiply by 0.971 per call, reset when the measurement mean changes
+    (reference solvers/equilibrium_solvers_yaping.py:409-413; BASELINE.md: 0.23529, 0.22847, 0.22184)."""
+    f = EquilibriumProxGradSCI(A_torch_, At_torch_, FFDNet(1, "ffdnet").eval(), 0.2)
+    y1, y2 = torch.full((1, 4, 4), 0.5), torch.full((1, 4, 4), 0.25)
+    s = [float(f._advance_sigma(y1)) for _ in range(3)]
+    ref = [np.float32(60 / 255)]
+    for _ in range(2):
+        ref.append(np.float32(ref[-1] * np.float32(0.971)))
+    assert s == [float(r) for r in ref]
+    assert abs(s[1] - 0.22847) < 1e-5 and abs(s[2] - 0.22184) < 1e-5
+    assert float(f._advance_sigma(y2)) == float(ref[0])          # new measurement: reset
+    assert float(f._advance_sigma(y2.clone())) == float(ref[1])  # same mean, other tensor: no reset
+    f.skip_call()
+    assert float(f._sigma) == float(ref[2])
+    assert f.noise_sigma.shape == (8,)
+
+
+def test_aliases_expose_reference_module_paths():
+    deqsci_b200.install_reference_aliases()
+    from solvers.equilibrium_solvers_yaping import EquilibriumProxGradSCI as E2
+    from solvers import new_equilibrium_utils_yaping as eq2
+    from utils.cg_utils import A_torch_ as A2
+    from networks.ffdnet.models import FFDNet as F2
+    from operators.operator import LinearOperator
+    assert E2 is EquilibriumProxGradSCI and A2 is A_torch_ and F2 is FFDNet
+    assert all(hasattr(eq2, n) for n in ("andersonexp", "anderson", "forward_iteration", "DEQFixedPoint"))
+    assert hasattr(LinearOperator, "gramian")
