@@ -42,6 +42,8 @@ SIGNATURES = {
                                        c_float, c_float, _P]),
     "deqsci_anderson_mix": (c_int, [_P, _P, _P, c_int, c_int, c_longlong, c_int, c_int, c_float, _P]),
     "deqsci_residual": (c_int, [_P, _P, _P, _P, c_longlong, c_float, _P]),
+    "deqsci_profile_begin": (c_int, [c_int]),
+    "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),
 }
 

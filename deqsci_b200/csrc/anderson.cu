@@ -274,11 +274,15 @@ extern "C" int deqsci_anderson_update(const float* X, const float* F, float* G, 
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = anderson_chunks(N);
   dim3 grid(chunks, B);
+  {
+  ProfScope prof(PK_AND_GRAM, st);
   if (vec4_ok(X, N) && vec4_ok(F, N) && vec4_ok(G, N))
     anderson_gram_kernel<4, true><<<grid, kGramThreads, 0, st>>>(X, F, G, scratch, B, N, slot, n);
   else
     anderson_gram_kernel<1, true><<<grid, kGramThreads, 0, st>>>(X, F, G, scratch, B, N, slot, n);
+  }
   DEQSCI_LAUNCH_CHECK();
+  ProfScope prof2(PK_AND_SOLVE, st);
   int threads = 32 * (B < 32 ? B : 32);
   anderson_solve_kernel<<<1, threads, 0, st>>>(scratch, gram, alpha, res, B, m, chunks, slot, n, lam, res_eps, 1);
   DEQSCI_LAUNCH_CHECK();
@@ -299,6 +303,7 @@ extern "C" int deqsci_anderson_mix(float* X, const float* F, const float* alpha,
   if (bx < 1) bx = 1;
   if (bx > 65535) bx = 65535;
   dim3 grid((unsigned)bx, B);
+  ProfScope prof(PK_AND_MIX, st);
   if (v4) anderson_mix_kernel<4><<<grid, threads, 0, st>>>(X, F, alpha, B, m, N, slot, n, beta);
   else    anderson_mix_kernel<1><<<grid, threads, 0, st>>>(X, F, alpha, B, m, N, slot, n, beta);
   DEQSCI_LAUNCH_CHECK();

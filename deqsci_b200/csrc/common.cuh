@@ -44,6 +44,16 @@ inline int num_sms() {
   return n;
 }
 
+// kernel classes for launch accounting / sampled event timing (profile.cu); order = deqsci.h
+enum ProfKind { PK_GAP = 0, PK_CONV_FIRST, PK_CONV_HIDDEN, PK_CONV_LAST, PK_AND_GRAM, PK_AND_SOLVE, PK_AND_MIX, PK_COUNT };
+struct ProfScope {
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+  int kind_;
+  cudaStream_t st_;
+  long long idx_;
+};
+
 // Activation storage between conv layers: channels-last [frames, H, W, 64], each value stored as
 // an fp16 pair  v ~= hi + lo * 2^-11  in two planes (hi plane then lo plane).  Keeps ~22 mantissa
 // bits (this split reproduces the fp32 trajectory at its noise floor) in exactly

@@ -354,6 +354,7 @@ int conv_first_launch(int kind, bool fuse_gap, const float* zin, const float* y,
   dim3 grid((Wc + TW - 1) / TW, (Hc + TH - 1) / TH, B);
   const size_t smem = first_smem_bytes(kind, T);
   DEQSCI_CHECK_ARG(smem <= 200 * 1024, "conv_first: T=%d needs %zu bytes of shared memory", T, smem);
+  ProfScope prof(PK_CONV_FIRST, st);
 #define LAUNCH_FIRST(K, F)                                                                                       \
   do {                                                                                                           \
     DEQSCI_CUDA(cudaFuncSetAttribute(conv_first_kernel<K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
@@ -379,6 +380,7 @@ int conv_mid_fp32_launch(const __half* act_in, __half* act_out, long long plane_
   DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long n_tiles = (long long)NF * ((Hc + TH - 1) / TH) * ((Wc + TW - 1) / TW);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  ProfScope prof(PK_CONV_HIDDEN, st);
   conv_mid_fp32_kernel<<<grid, kTileThreads, smem, st>>>(act_in, act_out, plane_elems, wpack, scale, bias, relu,
                                                          NF, Hc, Wc);
   DEQSCI_LAUNCH_CHECK();
@@ -394,6 +396,7 @@ int conv_last_launch(int kind, const __half* act_in, long long plane_elems, cons
   const size_t smem = sizeof(float) * ((size_t)9 * 64 * COUT + 8 + (size_t)(TH + 2) * (TW + 2) * kPixStride +
                                        (size_t)kTileThreads * COUT * T);
   DEQSCI_CHECK_ARG(smem <= 200 * 1024, "conv_last: T=%d needs %zu bytes of shared memory", T, smem);
+  ProfScope prof(PK_CONV_LAST, st);
   if (kind == DEQSCI_NET_FFDNET) {
     DEQSCI_CUDA(cudaFuncSetAttribute(conv_last_kernel<DEQSCI_NET_FFDNET>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

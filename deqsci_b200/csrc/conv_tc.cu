@@ -392,6 +392,7 @@ int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long l
   p.tiles_y = (Hc + THm - 1) / THm;
   p.n_tiles = (long long)NF * p.tiles_x * p.tiles_y;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+  ProfScope prof(PK_CONV_HIDDEN, st);
   if (split) {
     DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TcCfg<true>::kSmemBytes));

@@ -134,6 +134,7 @@ static int launch_gap(const float* a, const float* y, const float* phi, const fl
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool fast = (T == 8) && aligned16(phi) && aligned16(out) && (OP == OP_PHISUM || aligned16(a)) &&
                     (add == nullptr || aligned16(add));
+  ProfScope prof(PK_GAP, st);
   if (fast) {
     const long long n_items = n_pix * 2;
     long long blocks = (n_items + threads - 1) / threads;

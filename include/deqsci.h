@@ -156,6 +156,19 @@ int deqsci_residual(const float* a, const float* b, float* res, float* scratch, 
                     float res_eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Launch accounting and sampled device timing of the library's own kernels.
+ * Kernel classes: 0 gap, 1 conv_first, 2 conv_hidden, 3 conv_last, 4 anderson_gram,
+ * 5 anderson_solve, 6 anderson_mix  (DEQSCI_PROFILE_KINDS entries in every array below).
+ * deqsci_profile_begin resets the counters; with sample_every = k > 0 every k-th launch is bracketed
+ * by a pair of CUDA events on its own stream.  deqsci_profile_end synchronises the device and
+ * returns, per class, the summed milliseconds of the sampled launches, how many were sampled and
+ * how many were launched.
+ * ---------------------------------------------------------------------------------------------- */
+#define DEQSCI_PROFILE_KINDS 7
+int deqsci_profile_begin(int sample_every);
+int deqsci_profile_end(double* ms_sum, long long* n_sampled, long long* n_launched);
+
+/* ------------------------------------------------------------------------------------------------
  * Testing hook: runs ONE hidden 64->64 layer (index `layer`, 0 < layer < num_layers-1) of a plan on
  * caller-provided activation planes: channels-last [NF,Hc,Wc,64], fp16 hi plane followed by the
  * fp16 lo plane (value = hi + lo*2^-11).  Used by tests/ to compare the tcgen05 kernel against the
