@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("DEQSCI_BENCH_BATCH", 16)),
                     help="measurements per GPU per step")
     ap.add_argument("--precision", default="tc_split", choices=["tc_split", "fp32", "tc_single"])
-    ap.add_argument("--sample-every", type=int, default=16, help="event-time every k-th kernel launch")
+    ap.add_argument("--sample-every", type=int, default=11, help="event-time every k-th kernel launch")
     ap.add_argument("--cpu-iters", type=int, default=12, help="iterations of the CPU port sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

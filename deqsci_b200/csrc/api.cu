@@ -30,8 +30,11 @@ int conv_last_launch(int kind, const __half* act_in, long long plane_elems, cons
 int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long long plane_elems,
                        const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                        cudaStream_t st);
-size_t tc_weight_image_bytes(bool split);
-void tc_pack_weights(const float* w, bool split, uint8_t* img);
+int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, long long plane_elems,
+                   const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                   const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
+size_t tc_weight_image_bytes(bool split, int cout);
+void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img);
 
 struct Layer {
   int cin = 0, cout = 0, relu = 0;
@@ -116,11 +119,11 @@ extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layer
     rc = upload(pk.data(), pk.size() * sizeof(float), (void**)&L.w_cc);
     if (rc == DEQSCI_OK && S.scale_host) rc = upload(S.scale_host, S.cout * sizeof(float), (void**)&L.scale);
     if (rc == DEQSCI_OK && S.bias_host) rc = upload(S.bias_host, S.cout * sizeof(float), (void**)&L.bias);
-    const bool hidden = (i > 0 && i < num_layers - 1);
-    if (rc == DEQSCI_OK && hidden && precision != DEQSCI_PREC_FP32) {
+    // every layer with 64 input channels has a tensor-core image (hidden layers and the last layer)
+    if (rc == DEQSCI_OK && i > 0 && precision != DEQSCI_PREC_FP32) {
       const bool split = precision == DEQSCI_PREC_TC_SPLIT;
-      std::vector<uint8_t> img(tc_weight_image_bytes(split));
-      tc_pack_weights(S.weight_host, split, img.data());
+      std::vector<uint8_t> img(tc_weight_image_bytes(split, S.cout));
+      tc_pack_weights(S.weight_host, S.cout, split, img.data());
       rc = upload(img.data(), img.size(), (void**)&L.w_tc);
     }
   }
@@ -196,6 +199,10 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     cur ^= 1;
   }
   const Layer& LL = h->layers[nl - 1];
+  if (h->precision != DEQSCI_PREC_FP32)
+    return conv_tc_launch(h->kind == DEQSCI_NET_FFDNET ? 1 : 2, h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], nullptr,
+                          g.plane_elems, LL.w_tc, LL.scale, LL.bias, LL.relu, g.NF, g.Hc, g.Wc,
+                          fuse_gap ? zprime_ws : z, out, H, W, T, st);
   return conv_last_launch(h->kind, act[cur], g.plane_elems, LL.w_cc, LL.scale, LL.bias, LL.relu,
                           fuse_gap ? zprime_ws : z, out, B, H, W, T, st);
 }

@@ -20,6 +20,8 @@
 // Pipelines: smem A ring (full/empty mbarriers, tcgen05.commit frees a slot) and a double-buffered
 // TMEM accumulator (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>   // CUtensorMap types only; the encode entry point is fetched at run time
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -29,15 +31,32 @@ constexpr int kTileM = 128;
 constexpr int kTapBytesA = kTileM * 128;        // 16 KB: 128 pixels x 64 fp16
 constexpr int kTcThreads = 192;
 
-template <bool SPLIT>
+// HALO = true (tiles that are 128 consecutive pixels of one image row): a pipeline stage is one
+// input ROW with a one-pixel halo on each side (130 pixels, hi and lo planes) and the three kx taps
+// are three UMMA descriptors into it, 128 bytes (one pixel) apart -- 3 TMA row loads per tile instead
+// of 9 tap loads, which is what lifts the kernel off the L2->SM bandwidth roof.
+// HALO = false (small images, several rows per tile): one stage per tap, as loaded by TMA.
+// MODE: 0 = hidden layer (64 -> 64, writes activation planes);
+//       1 = FFDNet last layer (64 -> 4, pixel-shuffle, out = z' - noise in the cube layout);
+//       2 = DnCNN last layer (64 -> 1, out = z' - noise).  Last layers pad cout to N = 16.
+enum { TC_HIDDEN = 0, TC_LAST_FFD = 1, TC_LAST_DN = 2 };
+
+template <bool SPLIT, bool HALO, int MODE = TC_HIDDEN>
 struct TcCfg {
-  static constexpr int kBRows = SPLIT ? 128 : 64;             // rows of the B tile per tap
-  static constexpr int kTapBytesB = kBRows * 128;             // 16 KB / 8 KB
-  static constexpr int kWBytes = 9 * kTapBytesB;              // 144 KB / 72 KB
-  static constexpr int kStageBytes = SPLIT ? 2 * kTapBytesA : kTapBytesA;
-  static constexpr int kStages = SPLIT ? 2 : 6;
-  static constexpr int kAccCols = SPLIT ? 128 : 64;           // TMEM columns per accumulator buffer
-  static constexpr int kTmemCols = 2 * kAccCols;              // 256 / 128 (power of two >= 32)
+  static constexpr int kNOut = (MODE == TC_HIDDEN) ? 64 : 16; // UMMA N of one product (M = 128 needs N % 16 == 0)
+  static constexpr int kCout = (MODE == TC_HIDDEN) ? 64 : (MODE == TC_LAST_FFD ? 4 : 1);
+  static constexpr int kBRows = SPLIT ? 2 * kNOut : kNOut;    // rows of the B tile per tap: [hi | lo']
+  static constexpr int kTapBytesB = kBRows * 128;             // 16 KB / 8 KB (hidden)
+  static constexpr int kWBytes = 9 * kTapBytesB;              // 144 KB / 72 KB (hidden)
+  static constexpr int kRowPix = HALO ? kTileM + 2 : kTileM;  // pixels per stage plane
+  static constexpr int kPlaneBytes = HALO ? 17 * 1024 : kTapBytesA;   // 130*128 B rounded up to the 1 KB swizzle atom
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * kPlaneBytes;
+  static constexpr int kTxBytes = (SPLIT ? 2 : 1) * kRowPix * 128;     // bytes TMA delivers per stage
+  static constexpr int kSteps = HALO ? 3 : 9;                 // stages consumed per tile
+  static constexpr int kStagesFit = (227 * 1024 - 2048 - kWBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kAccCols = SPLIT ? 2 * kNOut : kNOut;  // TMEM columns per accumulator buffer
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two >= 32
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kWBytes + kStages * kStageBytes + 1024 /*barriers, affine*/;
 };
 
@@ -127,9 +146,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO=1024B | version 1 (sm_100) | layout 2
+// The 128-byte swizzle is a function of the absolute shared-memory address (bits 4-6 ^= bits 7-9), so
+// a start address kx*128 bytes into a TMA-written row buffer (the halo path) needs no base_offset:
+// measured on B200 -- base_offset = 0 is exact, base_offset = (addr >> 7) & 7 is wrong.
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
@@ -150,13 +178,17 @@ struct TcParams {
   int TWm, THm;             // tile = THm rows x TWm cols, TWm*THm == 128
   int tiles_x, tiles_y;
   long long n_tiles;
+  // last-layer modes: residual epilogue in the cube layout [B,H,W,T]
+  const float* zprime;
+  float* out_cube;
+  int H, W, T;
 };
 
-template <bool SPLIT>
+template <bool SPLIT, bool HALO, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                    const TcParams p) {
-  using Cfg = TcCfg<SPLIT>;
+  using Cfg = TcCfg<SPLIT, HALO, MODE>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -184,8 +216,9 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) {
     const int c = threadIdx.x - 64;
-    aff_s[c] = p.scale ? p.scale[c] : 1.f;
-    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+    const bool real = c < Cfg::kCout;
+    aff_s[c] = (real && p.scale) ? p.scale[c] : 1.f;
+    aff_s[64 + c] = (real && p.bias) ? p.bias[c] : 0.f;
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
   tc_fence_before();
@@ -206,13 +239,13 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         const int nf = (int)(tile / per_frame);
         const int rem = (int)(tile - (long long)nf * per_frame);
         const int h0 = (rem / p.tiles_x) * p.THm, w0 = (rem % p.tiles_x) * p.TWm;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - ky * 3;
+        for (int step = 0; step < Cfg::kSteps; ++step) {
+          const int ky = HALO ? step : step / 3, kx = HALO ? 0 : step - ky * 3;   // HALO: box starts at w0-1
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(bar_full(stage), Cfg::kStageBytes);
+          mbar_arrive_expect_tx(bar_full(stage), Cfg::kTxBytes);
           const uint32_t dst = smem_u32(a_s + stage * Cfg::kStageBytes);
           tma_load_4d(dst, &map_hi, bar_full(stage), 0, w0 + kx - 1, h0 + ky - 1, nf);
-          if (SPLIT) tma_load_4d(dst + kTapBytesA, &map_lo, bar_full(stage), 0, w0 + kx - 1, h0 + ky - 1, nf);
+          if (SPLIT) tma_load_4d(dst + Cfg::kPlaneBytes, &map_lo, bar_full(stage), 0, w0 + kx - 1, h0 + ky - 1, nf);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -220,8 +253,8 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_main = make_idesc(kTileM, SPLIT ? 128 : 64);
-      constexpr uint32_t idesc_lo = make_idesc(kTileM, 64);
+      constexpr uint32_t idesc_main = make_idesc(kTileM, Cfg::kBRows);
+      constexpr uint32_t idesc_lo = make_idesc(kTileM, Cfg::kNOut);
       mbar_wait(bar_w, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -231,17 +264,21 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         mbar_wait(bar_tempty(buf), tphase ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_main = tmem_base + buf * Cfg::kAccCols;
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int step = 0; step < Cfg::kSteps; ++step) {
           mbar_wait(bar_full(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_s + stage * Cfg::kStageBytes);
-          const uint64_t a_hi = make_sdesc(a_addr);
-          const uint64_t a_lo = make_sdesc(a_addr + kTapBytesA);
-          const uint64_t b_w = make_sdesc(smem_u32(w_s + tap * Cfg::kTapBytesB));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {               // K = 64 per tap = 4 x UMMA_K(16); +32 bytes per step
-            umma_f16(d_main, a_hi + 2 * k, b_w + 2 * k, idesc_main, (tap | k) != 0);
-            if (SPLIT) umma_f16(d_main + 64, a_lo + 2 * k, b_w + 2 * k, idesc_lo, 1u);
+          for (int sub = 0; sub < (HALO ? 3 : 1); ++sub) {   // HALO: the three kx taps share the row buffer
+            const int tap = HALO ? step * 3 + sub : step;
+            const uint64_t a_hi = make_sdesc(a_addr + sub * 128);
+            const uint64_t a_lo = make_sdesc(a_addr + Cfg::kPlaneBytes + sub * 128);
+            const uint64_t b_w = make_sdesc(smem_u32(w_s + tap * Cfg::kTapBytesB));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {             // K = 64 per tap = 4 x UMMA_K(16); +32 bytes per step
+              umma_f16(d_main, a_hi + 2 * k, b_w + 2 * k, idesc_main, (tap | k) != 0);
+              if (SPLIT) umma_f16(d_main + Cfg::kNOut, a_lo + 2 * k, b_w + 2 * k, idesc_lo, 1u);
+            }
           }
           umma_commit(bar_empty(stage));              // frees the smem slot when these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -267,6 +304,27 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       mbar_wait(bar_tfull(buf), tphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Cfg::kAccCols;
+      if (MODE != TC_HIDDEN) {
+        // last layer: cout values per pixel -> out = z' - noise, scattered through the pixel shuffle
+        uint32_t acc[4], cor[4];
+        tmem_ld4(t_addr, acc);
+        if (SPLIT) tmem_ld4(t_addr + Cfg::kNOut, cor);
+        tmem_ld_wait();
+        if (inside) {
+          const int b = nf / p.T, t = nf - b * p.T;
+#pragma unroll
+          for (int c = 0; c < Cfg::kCout; ++c) {
+            float a = __uint_as_float(acc[c]);
+            if (SPLIT) a = fmaf(__uint_as_float(cor[c]), kLoInvScale, a);
+            a = fmaf(a, aff_s[c], aff_s[64 + c]);
+            if (p.relu) a = fmaxf(a, 0.f);
+            long long g;
+            if (MODE == TC_LAST_FFD) g = (((long long)b * p.H + 2 * h + (c >> 1)) * p.W + 2 * w + (c & 1)) * p.T + t;
+            else                     g = (((long long)b * p.H + h) * p.W + w) * p.T + t;
+            p.out_cube[g] = __fsub_rn(p.zprime[g], a);
+          }
+        }
+      } else
 #pragma unroll
       for (int half = 0; half < 2; ++half) {          // 32 output channels at a time
         uint32_t acc[32], cor[32];
@@ -336,7 +394,8 @@ void tc_tile_shape(int Wc, int* TWm, int* THm) {
   *THm = kTileM / tw;
 }
 
-static int make_act_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int TWm, int THm) {
+static int make_act_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int box_w, int THm) {
+  const int TWm = box_w;
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
   cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
@@ -350,22 +409,29 @@ static int make_act_map(CUtensorMap* map, const __half* plane, int NF, int Hc, i
   return DEQSCI_OK;
 }
 
-size_t tc_weight_image_bytes(bool split) { return split ? TcCfg<true>::kWBytes : TcCfg<false>::kWBytes; }
+size_t tc_weight_image_bytes(bool split, int cout) {
+  const int n_out = cout == 64 ? 64 : 16;
+  return (size_t)9 * (split ? 2 : 1) * n_out * 128;
+}
 
-// Host packing of one hidden layer: w [64 cout][64 cin][3][3] fp32 -> the exact shared-memory image
-// the kernel bulk-copies: per tap a K-major tile [rows n][64 k=cin] fp16 with the 128-byte swizzle
-// (16-byte chunk index XOR (row & 7)); rows [0,64) = hi(W), rows [64,128) = lo'(W) (split mode).
-void tc_pack_weights(const float* w, bool split, uint8_t* img) {
-  const int rows = split ? 128 : 64;
+// Host packing of one layer: w [cout][64 cin][3][3] fp32 -> the exact shared-memory image the kernel
+// bulk-copies: per tap a K-major tile [rows n][64 k=cin] fp16 with the 128-byte swizzle (16-byte chunk
+// index XOR (row & 7)); rows [0,N) = hi(W) (zero rows for n >= cout), rows [N,2N) = lo'(W) (split
+// mode), N = 64 for hidden layers, 16 for the last layer.
+void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img) {
+  const int n_out = cout == 64 ? 64 : 16;
+  const int rows = split ? 2 * n_out : n_out;
+  memset(img, 0, (size_t)9 * rows * 128);
   for (int tap = 0; tap < 9; ++tap) {
     const int ky = tap / 3, kx = tap % 3;
     for (int n = 0; n < rows; ++n) {
-      const int co = n & 63;
+      const int co = n % n_out;
+      if (co >= cout) continue;
       for (int k = 0; k < 64; ++k) {
         const float v = w[((co * 64 + k) * 3 + ky) * 3 + kx];
         const __half hi = __float2half_rn(v);
         __half val = hi;
-        if (n >= 64) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
+        if (n >= n_out) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
         const size_t byte = (size_t)tap * rows * 128 + (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) +
                             (size_t)(k & 7) * 2;
         *reinterpret_cast<__half*>(img + byte) = val;
@@ -374,36 +440,67 @@ void tc_pack_weights(const float* w, bool split, uint8_t* img) {
   }
 }
 
-int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long long plane_elems,
-                       const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                       cudaStream_t st) {
+template <bool SPLIT, bool HALO, int MODE>
+static int launch_tc(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const TcParams& p, int grid,
+                     cudaStream_t st) {
+  using Cfg = TcCfg<SPLIT, HALO, MODE>;
+  DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<SPLIT, HALO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+  conv_mid_tc_kernel<SPLIT, HALO, MODE><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(map_hi, map_lo, p);
+  return DEQSCI_OK;
+}
+
+template <int MODE>
+static int launch_tc_mode(bool split, bool halo, const CUtensorMap& map_hi, const CUtensorMap& map_lo,
+                          const TcParams& p, int grid, cudaStream_t st) {
+  if (split) return halo ? launch_tc<true, true, MODE>(map_hi, map_lo, p, grid, st)
+                         : launch_tc<true, false, MODE>(map_hi, map_lo, p, grid, st);
+  return halo ? launch_tc<false, true, MODE>(map_hi, map_lo, p, grid, st)
+              : launch_tc<false, false, MODE>(map_hi, map_lo, p, grid, st);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// mode: TC_HIDDEN writes act_out planes; TC_LAST_* writes out_cube = zprime - noise ([B,H,W,T] fp32).
+int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, long long plane_elems,
+                   const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                   const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st) {
   int TWm, THm;
   tc_tile_shape(Wc, &TWm, &THm);
+  // row-halo pipeline whenever a tile is one 128-pixel row segment (DEQSCI_TC_HALO=0 forces per-tap loads)
+  static const int halo_env = env_int("DEQSCI_TC_HALO", 1);
+  const bool halo = (TWm == kTileM) && halo_env != 0;
   CUtensorMap map_hi, map_lo;
-  int rc = make_act_map(&map_hi, act_in, NF, Hc, Wc, TWm, THm);
+  int rc = make_act_map(&map_hi, act_in, NF, Hc, Wc, halo ? kTileM + 2 : TWm, THm);
   if (rc) return rc;
-  rc = make_act_map(&map_lo, act_in + plane_elems, NF, Hc, Wc, TWm, THm);
+  rc = make_act_map(&map_lo, act_in + plane_elems, NF, Hc, Wc, halo ? kTileM + 2 : TWm, THm);
   if (rc) return rc;
   TcParams p;
   p.wimg = wimg; p.scale = scale; p.bias = bias;
-  p.out_hi = act_out; p.out_lo = act_out + plane_elems;
+  p.out_hi = act_out; p.out_lo = act_out ? act_out + plane_elems : nullptr;
   p.relu = relu; p.NF = NF; p.Hc = Hc; p.Wc = Wc; p.TWm = TWm; p.THm = THm;
   p.tiles_x = (Wc + TWm - 1) / TWm;
   p.tiles_y = (Hc + THm - 1) / THm;
   p.n_tiles = (long long)NF * p.tiles_x * p.tiles_y;
+  p.zprime = zprime; p.out_cube = out_cube; p.H = H; p.W = W; p.T = T;
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-  ProfScope prof(PK_CONV_HIDDEN, st);
-  if (split) {
-    DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TcCfg<true>::kSmemBytes));
-    conv_mid_tc_kernel<true><<<grid, kTcThreads, TcCfg<true>::kSmemBytes, st>>>(map_hi, map_lo, p);
-  } else {
-    DEQSCI_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TcCfg<false>::kSmemBytes));
-    conv_mid_tc_kernel<false><<<grid, kTcThreads, TcCfg<false>::kSmemBytes, st>>>(map_hi, map_lo, p);
-  }
+  ProfScope prof(mode == TC_HIDDEN ? PK_CONV_HIDDEN : PK_CONV_LAST, st);
+  if (mode == TC_HIDDEN) rc = launch_tc_mode<TC_HIDDEN>(split, halo, map_hi, map_lo, p, grid, st);
+  else if (mode == TC_LAST_FFD) rc = launch_tc_mode<TC_LAST_FFD>(split, halo, map_hi, map_lo, p, grid, st);
+  else rc = launch_tc_mode<TC_LAST_DN>(split, halo, map_hi, map_lo, p, grid, st);
+  if (rc) return rc;
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
+}
+
+int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long long plane_elems,
+                       const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                       cudaStream_t st) {
+  return conv_tc_launch(TC_HIDDEN, split, act_in, act_out, plane_elems, wimg, scale, bias, relu, NF, Hc, Wc,
+                        nullptr, nullptr, 0, 0, 1, st);
 }
 
 }  // namespace deqsci
