@@ -33,13 +33,20 @@ int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long l
 int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, long long plane_elems,
                    const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                    const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
+size_t tc2_weight_image_bytes();
+void tc2_pack_weights(const float* w, uint8_t* img);
+bool tc2_supported(int Hc, int Wc);
+int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
+                            const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                            cudaStream_t st);
 size_t tc_weight_image_bytes(bool split, int cout);
 void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img);
 
 struct Layer {
   int cin = 0, cout = 0, relu = 0;
   float* w_cc = nullptr;      // CUDA-core packing [9][cin][cout] fp32
-  uint8_t* w_tc = nullptr;    // tcgen05 shared-memory image (hidden layers, TC modes)
+  uint8_t* w_tc = nullptr;    // tcgen05 shared-memory image (hidden and last layers, TC modes)
+  uint8_t* w_tc2 = nullptr;   // CTA-pair image (hidden layers, split precision)
   float* scale = nullptr;     // [cout] or null
   float* bias = nullptr;      // [cout] or null
 };
@@ -63,6 +70,7 @@ extern "C" int deqsci_denoiser_destroy(deqsci_denoiser* h) {
   for (auto& L : h->layers) {
     if (L.w_cc) cudaFree(L.w_cc);
     if (L.w_tc) cudaFree(L.w_tc);
+    if (L.w_tc2) cudaFree(L.w_tc2);
     if (L.scale) cudaFree(L.scale);
     if (L.bias) cudaFree(L.bias);
   }
@@ -125,6 +133,11 @@ extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layer
       std::vector<uint8_t> img(tc_weight_image_bytes(split, S.cout));
       tc_pack_weights(S.weight_host, S.cout, split, img.data());
       rc = upload(img.data(), img.size(), (void**)&L.w_tc);
+      if (rc == DEQSCI_OK && split && S.cout == kHidden) {
+        std::vector<uint8_t> img2(tc2_weight_image_bytes());
+        tc2_pack_weights(S.weight_host, img2.data());
+        rc = upload(img2.data(), img2.size(), (void**)&L.w_tc2);
+      }
     }
   }
   if (rc != DEQSCI_OK) {
@@ -192,6 +205,9 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     if (h->precision == DEQSCI_PREC_FP32)
       rc = conv_mid_fp32_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
                                 g.Wc, st);
+    else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))
+      rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, L.scale, L.bias, L.relu, g.NF,
+                                   g.Hc, g.Wc, st);
     else
       rc = conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], act[cur ^ 1], g.plane_elems, L.w_tc,
                               L.scale, L.bias, L.relu, g.NF, g.Hc, g.Wc, st);
@@ -232,6 +248,9 @@ extern "C" int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, co
   if (h->precision == DEQSCI_PREC_FP32)
     return conv_mid_fp32_launch((const __half*)act_in, (__half*)act_out, plane, L.w_cc, L.scale, L.bias, L.relu, NF,
                                 Hc, Wc, st);
+  if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(Hc, Wc))
+    return conv_hidden_2cta_launch((const __half*)act_in, (__half*)act_out, plane, L.w_tc2, L.scale, L.bias, L.relu,
+                                   NF, Hc, Wc, st);
   return conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, (const __half*)act_in, (__half*)act_out, plane,
                             L.w_tc, L.scale, L.bias, L.relu, NF, Hc, Wc, st);
 }

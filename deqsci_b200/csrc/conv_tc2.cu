@@ -1,0 +1,499 @@
+// Kernel group 2c: hidden 64->64 3x3 conv layer, split-fp16 precision, as a CTA-PAIR kernel
+// (thread-block cluster of 2, tcgen05 cta_group::2, UMMA_M = 256).
+//
+// Why a pair: the split-precision weights [Wh | Wl'] of one layer are 144 KB.  Resident in ONE CTA
+// they leave room for only two activation-row slots and no store staging, so the single-CTA kernel
+// (conv_tc.cu, LD_ROW3) is starved by TMA latency and its epilogue pays 32 partial-line stores per
+// instruction.  cta_group::2 lets each CTA of the pair keep HALF of the B operand (72 KB): that
+// frees shared memory for a 4-slot rolling row ring (every input row is loaded once per strip and
+// used by the three output rows around it) plus staging buffers for coalesced TMA stores, and halves
+// the B-operand shared-memory reads per SM.
+//
+// Each CTA of the pair owns its own strip of R consecutive output rows (128-pixel row segments) of
+// some frame; the two strips only share the weights.  Per output row and CTA:
+//     MMA 1: A = Ah (own 128 pixels), B = 128 rows (64 from each CTA), N = 128
+//     MMA 2: A = Al',                 B =  64 rows (32 from each CTA), N =  64
+// B rows are interleaved so both instructions find their half at the SAME smem address in each CTA:
+//     leader tile rows [0,32) = Wh[0:32], [32,64) = Wl'[0:32];  peer: Wh[32:64], Wl'[32:64]
+//   => MMA 1 columns: [0,32) main 0-31 | [32,64) corr1 0-31 | [64,96) main 32-63 | [96,128) corr1 32-63
+//      MMA 2 columns: [128,192) corr2 0-63           out = main + 2^-11 (corr1 + corr2)
+//
+// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM alloc (+ MMA issuer in the
+// leader CTA only), warps 2-9 epilogue (TMEM lane quarter = warp % 4, channel half = (warp-2) / 4).
+// Barriers: full[s] lives in the leader (both CTAs' TMA loads complete_tx on it), empty[s] and
+// tmem_full[b] in both CTAs (multicast tcgen05.commit), tmem_empty[b] in the leader (16 arrivals).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace deqsci {
+
+namespace tc2 {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;
+constexpr int kSlots = 4;                         // rolling ring of input rows
+constexpr int kPlaneBytes = 17 * 1024;            // 130 pixels x 128 B, rounded up to the 1 KB swizzle atom
+constexpr int kSlotBytes = 2 * kPlaneBytes;       // hi + lo
+constexpr int kTxBytes = 2 * (kTileM + 2) * 128;  // bytes one CTA's TMA delivers per row
+constexpr int kTapBytesB = 64 * 128;              // this CTA's half of the B tile of one tap
+constexpr int kWBytes = 9 * kTapBytesB;           // 72 KB per CTA
+constexpr int kStageBytes = 2048;                 // per epilogue warp: 32 pixels x 32 channels fp16
+constexpr int kAccCols = 192;                     // main/corr1 interleaved (128) + corr2 (64)
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One lane of a converged warp.  ptxas knows a region guarded by elect.sync has a single active
+// thread, so descriptor operands move to uniform registers directly; guarding with `lane == 0`
+// instead makes it wrap EVERY tcgen05.mma / TMA instruction in a uniformisation loop
+// (ELECT + R2UR.BROADCAST + BRA.U.ANY), which cost ~100 cycles per MMA.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `local_addr`'s twin in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier anywhere in the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();      // a pipeline bug becomes a launch error, not a hang
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMA row load into THIS CTA's shared memory, completing on `cluster_bar` (the leader's full barrier)
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread retired) on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {   // K-major, SWIZZLE_128B (see conv_tc.cu)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Params {
+  const uint8_t* wimg;        // [2 ranks][9 taps][64 rows][128 B]
+  const float* scale;
+  const float* bias;
+  int relu;
+  int NF, Hc, Wc;
+  int tiles_x, strips_y, strip_rows;
+  long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
+  long long n_pair_items;
+};
+
+struct Strip { int nf, h0, w0; bool real; };
+
+__device__ __forceinline__ Strip decode(const Params& p, long long strip) {
+  Strip s;
+  s.real = strip < p.n_strips;
+  if (!s.real) strip = p.n_strips - 1;
+  const int per_frame = p.tiles_x * p.strips_y;
+  s.nf = (int)(strip / per_frame);
+  const int rem = (int)(strip - (long long)s.nf * per_frame);
+  const int sy = rem / p.tiles_x;
+  s.w0 = (rem - sy * p.tiles_x) * kTileM;
+  s.h0 = sy * p.strip_rows;
+  return s;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
+                        const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
+                        const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_s = smem;
+  uint8_t* a_s = w_s + kWBytes;
+  uint8_t* st_s = a_s + kSlots * kSlotBytes;                 // 8 x 2 KB store staging
+  uint8_t* tail = st_s + 8 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);        // [0] w, full[4], empty[4], tfull[2], tempty[2]
+  float* aff_s = reinterpret_cast<float*>(tail + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlots + s]); };
+  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlots + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[3 + 2 * kSlots + b]); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 16); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int c = threadIdx.x - 64;
+    aff_s[c] = p.scale ? p.scale[c] : 1.f;
+    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 0 && elect_one_sync()) {
+    // this CTA's half of the weights; visible to the pair after the cluster barrier below
+    mbar_arrive_expect_tx(bar_w, kWBytes);
+    const uint8_t* src = p.wimg + (size_t)rank * kWBytes;
+    for (int t = 0; t < 9; ++t) bulk_load_1d(smem_u32(w_s + t * kTapBytesB), src + (size_t)t * kTapBytesB, kTapBytesB, bar_w);
+    mbar_wait(bar_w, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                 // both CTAs: barriers initialised, weights resident, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own rows) =====================
+    if (elect_one_sync()) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+        const Strip s = decode(p, 2 * item + rank);
+        for (int q = 0; q < p.strip_rows + 2; ++q) {
+          mbar_wait(bar_empty(slot), phase ^ 1);
+          const uint32_t full_leader = mapa(bar_full(slot), 0);
+          if (leader) mbar_arrive_expect_tx(bar_full(slot), 2 * kTxBytes);   // both CTAs' rows complete here
+          const uint32_t dst = smem_u32(a_s + slot * kSlotBytes);
+          tma_load_4d_2cta(dst, &in_hi, full_leader, 0, s.w0 - 1, s.h0 - 1 + q, s.nf);
+          tma_load_4d_2cta(dst + kPlaneBytes, &in_lo, full_leader, 0, s.w0 - 1, s.h0 - 1 + q, s.nf);
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread, for the pair) =====================
+    if (leader && elect_one_sync()) {
+      constexpr uint32_t idesc_main = make_idesc(256, 128);
+      constexpr uint32_t idesc_lo = make_idesc(256, 64);
+      const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
+      int first = 0;                 // slot of the strip's first row
+      uint32_t first_phase = 0;
+      int buf = 0;
+      uint32_t tphase = 0;
+      for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+        int wait_slot = first;
+        uint32_t wait_phase = first_phase;
+        int rows_ready = 0;
+        for (int j = 0; j < p.strip_rows; ++j) {
+          mbar_wait(bar_tempty(buf), tphase ^ 1);
+          while (rows_ready < j + 3) {               // output row j needs input rows j, j+1, j+2
+            mbar_wait(bar_full(wait_slot), wait_phase);
+            if (++wait_slot == kSlots) { wait_slot = 0; wait_phase ^= 1; }
+            ++rows_ready;
+          }
+          tc_fence_after();
+          const uint32_t d_main = tmem_base + buf * kAccCols;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int slot = (first + j + ky) % kSlots;
+            const uint32_t a_row = a_base + slot * kSlotBytes;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int tap = ky * 3 + kx;
+              const uint64_t a_hi = make_sdesc(a_row + kx * 128);
+              const uint64_t a_lo = make_sdesc(a_row + kPlaneBytes + kx * 128);
+              const uint64_t b_w = make_sdesc(w_base + tap * kTapBytesB);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma2_f16(d_main, a_hi + 2 * k, b_w + 2 * k, idesc_main, (tap | k) != 0);
+                umma2_f16(d_main + 128, a_lo + 2 * k, b_w + 2 * k, idesc_lo, (tap | k) != 0);
+              }
+            }
+          }
+          const int dead = (first + j) % kSlots;
+          umma2_commit_mc(bar_empty(dead));          // input row j is dead after output row j (both CTAs)
+          if (j == p.strip_rows - 1) {
+            umma2_commit_mc(bar_empty((dead + 1) % kSlots));
+            umma2_commit_mc(bar_empty((dead + 2) % kSlots));
+          }
+          umma2_commit_mc(bar_tfull(buf));
+          if (++buf == 2) { buf = 0; tphase ^= 1; }
+        }
+        first = wait_slot;
+        first_phase = wait_phase;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int e = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    const int half = e >> 2;                      // output channels [32*half, +32)
+    const uint32_t stage = smem_u32(st_s + e * kStageBytes);
+    const uint32_t tempty_leader0 = mapa(bar_tempty(0), 0), tempty_leader1 = mapa(bar_tempty(1), 0);
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+      const Strip s = decode(p, 2 * item + rank);
+      for (int j = 0; j < p.strip_rows; ++j) {
+        const int h = s.h0 + j;
+        mbar_wait(bar_tfull(buf), tphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
+        uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {      // 16 channels at a time
+          uint32_t acc[16], c1[16], c2[16];
+          tmem_ld16(t_row + half * 64 + part * 16, acc);
+          tmem_ld16(t_row + half * 64 + 32 + part * 16, c1);
+          tmem_ld16(t_row + 128 + half * 32 + part * 16, c2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int c = half * 32 + part * 16 + i + u;
+              float a = fmaf(__uint_as_float(c1[i + u]) + __uint_as_float(c2[i + u]), kLoInvScale,
+                             __uint_as_float(acc[i + u]));
+              a = fmaf(a, aff_s[c], aff_s[64 + c]);
+              v[u] = p.relu ? fmaxf(a, 0.f) : a;
+            }
+            __half h0, l0, h1, l1;
+            split_f16(v[0], h0, l0);
+            split_f16(v[1], h1, l1);
+            hi_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+        }
+        // accumulator drained: hand the TMEM buffer back to the leader's MMA thread
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf == 0 ? tempty_leader0 : tempty_leader1);
+        // stage (64-byte swizzle: chunk ^= (row >> 1) & 3) and store the two planes with TMA
+        const uint32_t row_addr = stage + lane * 64;
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
+          if (lane == 0) bulk_wait_read0();          // previous store has finished reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((q ^ sw) << 4)), "r"(pk[4 * q]),
+                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && s.real) {
+            tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, s.w0 + quarter * 32, h, s.nf);
+            bulk_commit();
+          }
+        }
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                 // the peer may still be reading this CTA's weights / barriers until here
+  if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
+}  // namespace tc2
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled2 get_encode2() {
+  static PFN_encodeTiled2 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled2>(ptr);
+  }
+  return fn;
+}
+
+static int make_plane_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int box_c, int box_w,
+                          CUtensorMapSwizzle sw) {
+  PFN_encodeTiled2 enc = get_encode2();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
+  cuuint64_t strides[3] = {128, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
+  return DEQSCI_OK;
+}
+
+size_t tc2_weight_image_bytes() { return 2 * (size_t)tc2::kWBytes; }
+
+// w [64 cout][64 cin][3][3] fp32 -> [rank][tap][64 rows][128 B], rows of rank r: [0,32) = hi(W[32r + n]),
+// [32,64) = lo'(W[32r + n - 32]); K-major fp16 rows with the 128-byte swizzle.
+void tc2_pack_weights(const float* w, uint8_t* img) {
+  for (int rank = 0; rank < 2; ++rank)
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      for (int n = 0; n < 64; ++n) {
+        const int co = 32 * rank + (n & 31);
+        for (int k = 0; k < 64; ++k) {
+          const float v = w[((co * 64 + k) * 3 + ky) * 3 + kx];
+          const __half hi = __float2half_rn(v);
+          __half val = hi;
+          if (n >= 32) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
+          const size_t byte = ((size_t)rank * 9 + tap) * tc2::kTapBytesB + (size_t)n * 128 +
+                              (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+          *reinterpret_cast<__half*>(img + byte) = val;
+        }
+      }
+    }
+}
+
+// true when the pair kernel can run this shape: full 128-pixel row tiles and a strip height that divides Hc
+bool tc2_supported(int Hc, int Wc) {
+  static const int enabled = getenv("DEQSCI_TC_PAIR") ? atoi(getenv("DEQSCI_TC_PAIR")) : 1;
+  return enabled && Wc > 64 && Hc % 2 == 0;
+}
+
+int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
+                            const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                            cudaStream_t st) {
+  tc2::Params p;
+  p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
+  p.NF = NF; p.Hc = Hc; p.Wc = Wc;
+  p.tiles_x = (Wc + tc2::kTileM - 1) / tc2::kTileM;
+  const int pairs_hw = num_sms() / 2;
+  // strip height: the largest power of two <= 16 dividing Hc that still leaves >= 6 pair-items per SM pair
+  int R = 16;
+  while (R > 1 && (Hc % R != 0 || (long long)NF * p.tiles_x * (Hc / R) < 12LL * pairs_hw)) R /= 2;
+  p.strip_rows = R;
+  p.strips_y = Hc / R;
+  p.n_strips = (long long)NF * p.tiles_x * p.strips_y;
+  p.n_pair_items = (p.n_strips + 1) / 2;
+  CUtensorMap in_hi, in_lo, out_hi, out_lo;
+  int rc;
+  if ((rc = make_plane_map(&in_hi, act_in, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_plane_map(&in_lo, act_in + plane_elems, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_plane_map(&out_hi, act_out, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
+  DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   tc2::kSmemBytes));
+  ProfScope prof(PK_CONV_HIDDEN, st);
+  tc2::conv_hidden_2cta_kernel<<<(unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st>>>(in_hi, in_lo, out_hi,
+                                                                                               out_lo, p);
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+}  // namespace deqsci

@@ -122,7 +122,8 @@ def _join_planes(p):
     return p[0].float() + p[1].float() / 2048.0
 
 
-@pytest.mark.parametrize("NF,Hc,Wc", [(2, 16, 16), (3, 9, 24), (1, 5, 130), (8, 128, 128), (2, 64, 256)])
+@pytest.mark.parametrize("NF,Hc,Wc", [(2, 16, 16), (3, 9, 24), (1, 5, 130), (8, 128, 128), (2, 64, 256),
+                                      (1, 6, 128), (3, 10, 200), (5, 32, 65)])
 @pytest.mark.parametrize("precision", ["tc_split", "fp32"])
 def test_hidden_layer_vs_fp64_conv(dev, NF, Hc, Wc, precision):
     """One 64->64 layer (tcgen05 split-fp16 kernel and the fp32 CUDA-core kernel) against
