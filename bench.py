@@ -198,7 +198,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     B = args.batch
     solver, deq = build_deq(dev, args.precision)
-    y_h, phi_h, gt = synthetic_batch(rank * B, B)     # contiguous index range per rank
+    from deqsci_b200.distributed import shard_range
+    lo, hi = shard_range(world * B, rank, world)      # contiguous index range per rank, no collective
+    y_h, phi_h, gt = synthetic_batch(lo, hi - lo)
     y_h, phi_h = y_h.pin_memory(), phi_h.pin_memory()
     out_h = torch.empty(B, H, W, T).pin_memory()
     y_d, phi_d = y_h.to(dev), phi_h.to(dev)
@@ -289,9 +291,14 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(y_h.numel() * 4 + phi_h.numel() * 4),
                 "d2h_bytes_per_step": int(out_h.numel() * 4)},
         "gpu_launches": int(sum(n_launch)),
-        "roofline": {"kernel": "conv_mid_tc_kernel<split> (hidden 64->64 3x3 layer, tcgen05)", "bound": "tensor",
+        "roofline": {"kernel": "conv_hidden_2cta_kernel (hidden 64->64 3x3 layer, tcgen05 cta_group::2)"
+                               if args.precision == "tc_split" else "conv_mid_tc_kernel (hidden layer)",
+                     "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "peak_source": peak_src + ", bf16 dense sustained",
+                     # dram read+write per launch from the ncu --set full capture in profiles/ (B=8: 497.8 MB)
+                     "traffic": 497.8e6 / 8 * B if args.precision == "tc_split" else None,
+                     "traffic_unit": "bytes per launch (profiles/r01_kernel_metrics.md, scaled by batch)",
+                     "peak_source": peak_src + ", bf16 dense sustained",
                      "avg_launch_ms": hid_ms, "algorithmic_flop_per_launch": flop_per_launch,
                      "issued_mma_flop_factor": 3 if args.precision == "tc_split" else 1,
                      "sampled_launches": int(n_samp[2])},

@@ -16,6 +16,7 @@ _ALIASES = [
     "networks.ffdnet.models", "networks.ffdnet.functions", "networks.provable", "networks.provable.model",
     "networks.provable.model.SimpleCNN_models", "networks.provable.model.conv_sn_chen", "solvers",
     "solvers.equilibrium_solvers_yaping", "solvers.new_equilibrium_utils_yaping",
+    "training", "training.sci_equilibrium_training", "utils.sci_dataloader", "utils.metrics",
 ]
 
 

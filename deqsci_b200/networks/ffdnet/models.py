@@ -103,7 +103,9 @@ class FFDNet(nn.Module, NativePlanCache):
         return "ffdnet", sequential_to_plan_layers(self.intermediate_dncnn.itermediate_dncnn)
 
     def uses_native(self, x):
-        return x.is_cuda and self.num_input_channels == 1 and not (self.training and torch.is_grad_enabled())
+        # train mode means batch-statistics BatchNorm (and running-stat updates) on every call, which
+        # the folded-BN plan does not express: the native path is the eval-mode network.
+        return x.is_cuda and self.num_input_channels == 1 and not self.training
 
     def forward(self, x, noise_sigma):
         if self.uses_native(x):

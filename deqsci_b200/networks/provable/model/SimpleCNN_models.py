@@ -43,8 +43,15 @@ class DnCNN(nn.Module, NativePlanCache):
             raise DeqsciError("the native DnCNN path covers single-channel frames (the SCI path)")
         return "dncnn", sequential_to_plan_layers(self.dncnn)
 
+    def _stateless_in_train_mode(self):
+        return all(isinstance(m, (nn.Conv2d, nn.ReLU)) for m in self.dncnn)
+
     def uses_native(self, x):
-        return x.is_cuda and self.channels == 1 and not (self.training and torch.is_grad_enabled())
+        # eval mode always; train mode only under no_grad for plain conv/ReLU stacks (BatchNorm batch
+        # statistics and the spectral-norm power iteration are per-call state the plan does not express)
+        if not (x.is_cuda and self.channels == 1):
+            return False
+        return (not self.training) or (not torch.is_grad_enabled() and self._stateless_in_train_mode())
 
     def forward(self, x):
         if self.uses_native(x):

@@ -337,3 +337,43 @@ def test_full_scene_psnr_vs_reference(dev, full_recon, d, scene):
     assert abs(ssim - float(full_recon[key + "_ssim"])) <= 1e-3
     crop = z[0, 96:160, 96:160].cpu().numpy()
     assert rel_l2(crop, full_recon[key + "_z_crop"]) <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# (6) the caller: test_solver_sci over all benchmark scenes present (configs 2 and 3)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", DENOISERS)
+def test_solver_sci_all_scenes_vs_reference(dev, full_recon, d):
+    """All 8 benchmark measurements (drop8, runner8, traffic x6) through the mirrored
+    test_solver_sci, every measurement's PSNR within 0.05 dB / SSIM within 1e-3 of the reference run,
+    and the reported average equal to the reference's."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.training import sci_equilibrium_training as tr
+    from deqsci_b200.utils.metrics import peak_signal_noise_ratio, ssim
+    solver = build_solver(d, dev)
+    max_iter = 180 if d == "ffdnet" else 100
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=max_iter, tol=1e-5)
+    samples, want_scene = [], []
+    for scene in ["drop8", "runner8", "traffic"]:
+        gt, mask, meas = load_scene(scene)
+        if scene in ("drop8", "runner8"):
+            meas = np.concatenate([meas] + [meas[:, :, :1]] * 4, axis=2)     # the .mat files carry 5 measurements
+        samples.append({"gt": torch.from_numpy(gt)[None], "mask": torch.from_numpy(mask)[None],
+                        "meas": torch.from_numpy(meas)[None], "file": [scene + "_cacti.mat"]})
+        n = 1 if scene != "traffic" else 6
+        want_scene.append(np.mean([float(full_recon["%s_%s_%d_psnr" % (d, scene, i)]) for i in range(n)]))
+    avg, images = tr.test_solver_sci(deq, samples, save_img_path=None, verbose=False, save_image=False, device=dev)
+    assert abs(avg - float(np.mean(want_scene))) <= 0.05
+    assert len(images) == 8 * 8                                   # one [H,W,1] array per frame
+    k0 = "drop8_cacti.mat_reconstruction_0.png"
+    assert images[k0].shape == (256, 256, 1) and images[k0].max() <= 255.0
+    # per-measurement PSNR / SSIM from the returned frames
+    gt, _, _ = load_scene("traffic")
+    for fi in range(6):
+        rec = np.stack([images["traffic_cacti.mat_reconstruction_%d.png" % (fi * 8 + t)][:, :, 0] for t in range(8)],
+                       axis=2) / 255.0
+        g = gt[:, :, fi * 8:(fi + 1) * 8]
+        assert abs(peak_signal_noise_ratio(g, rec) - float(full_recon["%s_traffic_%d_psnr" % (d, fi)])) <= 0.05
+        s = float(ssim(torch.from_numpy(rec.astype(np.float32)).permute(2, 0, 1)[None],
+                       torch.from_numpy(g).permute(2, 0, 1)[None]))
+        assert abs(s - float(full_recon["%s_traffic_%d_ssim" % (d, fi)])) <= 1e-3
