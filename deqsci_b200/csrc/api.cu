@@ -33,6 +33,15 @@ int conv_mid_tc_launch(bool split, const __half* act_in, __half* act_out, long l
 int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, long long plane_elems,
                    const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                    const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
+int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
+                    float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
+                    int T, bool do_gap, cudaStream_t st);
+size_t tcf_weight_image_bytes();
+void tcf_pack_weights(const float* w, int cin, uint8_t* img);
+bool tcf_supported(int Wc);
+int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
+                         const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
+                         int Wc, cudaStream_t st);
 size_t tc2_weight_image_bytes();
 void tc2_pack_weights(const float* w, uint8_t* img);
 bool tc2_supported(int Hc, int Wc);
@@ -127,6 +136,11 @@ extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layer
     rc = upload(pk.data(), pk.size() * sizeof(float), (void**)&L.w_cc);
     if (rc == DEQSCI_OK && S.scale_host) rc = upload(S.scale_host, S.cout * sizeof(float), (void**)&L.scale);
     if (rc == DEQSCI_OK && S.bias_host) rc = upload(S.bias_host, S.cout * sizeof(float), (void**)&L.bias);
+    if (rc == DEQSCI_OK && i == 0 && precision != DEQSCI_PREC_FP32) {     // first layer: K padded to 16 per tap
+      std::vector<uint8_t> img(tcf_weight_image_bytes());
+      tcf_pack_weights(S.weight_host, S.cin, img.data());
+      rc = upload(img.data(), img.size(), (void**)&L.w_tc);
+    }
     // every layer with 64 input channels has a tensor-core image (hidden layers and the last layer)
     if (rc == DEQSCI_OK && i > 0 && precision != DEQSCI_PREC_FP32) {
       const bool split = precision == DEQSCI_PREC_TC_SPLIT;
@@ -196,8 +210,18 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   cudaStream_t st = (cudaStream_t)stream;
   const int nl = (int)h->layers.size();
   const Layer& L0 = h->layers[0];
-  rc = conv_first_launch(h->kind, fuse_gap, z, y, phi, phi_sum, zprime_ws, sigma, L0.w_cc, L0.scale, L0.bias,
-                         L0.relu, act[0], g.plane_elems, B, H, W, T, st);
+  if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
+    // tensor-core first layer: GAP + unshuffle + split into 16-channel planes (parked in the second
+    // ping-pong buffer, which is free until the first hidden layer writes it), then the MMA kernel
+    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * 16;
+    rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap, st);
+    if (rc) return rc;
+    rc = conv_first_tc_launch(act[1], in_plane, act[0], g.plane_elems, L0.w_tc, L0.scale, L0.bias, L0.relu, g.NF,
+                              g.Hc, g.Wc, st);
+  } else {
+    rc = conv_first_launch(h->kind, fuse_gap, z, y, phi, phi_sum, zprime_ws, sigma, L0.w_cc, L0.scale, L0.bias,
+                           L0.relu, act[0], g.plane_elems, B, H, W, T, st);
+  }
   if (rc) return rc;
   int cur = 0;
   for (int i = 1; i < nl - 1; ++i) {

@@ -1,0 +1,322 @@
+// Kernel group 2d: the FIRST conv layer of the denoiser on tensor cores (split-fp16 precision).
+//
+// Input: the 16-channel planes written by gap_prep_kernel (gap.cu): channels-last [frames,Hc,Wc,16],
+// FFDNet = {sigma, 4 unshuffled sub-pixels, 0 x 11}, DnCNN = {pixel, 0 x 15}.  K per tap is padded to
+// one UMMA_K (16), so a tile costs 9 taps x (N=128 + N=64) = 864 MMA cycles instead of the 2880 FMA
+// cycles per pixel-row the CUDA-core kernel needs, and the K = 45 / 9 gather disappears: a tap is a
+// UMMA descriptor 32 bytes (one pixel) further into a TMA-loaded input row (32-byte swizzle).
+//
+// Structure = the rolling-row pipeline of conv_tc.cu (LD_ROLL) with the epilogue of conv_tc2.cu:
+// warp 0 TMA producer (6-slot ring of input rows with 1-pixel halo, hi + lo planes), warp 1 TMEM
+// allocator + MMA issuer, warps 2-9 epilogue (tcgen05.ld -> affine + ReLU -> hi/lo split -> swizzled
+// smem -> TMA store of 32 pixels x 32 channels per warp and plane).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace deqsci {
+namespace tcf {
+using namespace ptx;
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;
+constexpr int kSlots = 6;
+constexpr int kRowBytes = 32;                                  // 16 channels fp16
+constexpr int kPlaneBytes = 5 * 1024;                          // 130 pixels x 32 B = 4160 B, padded
+constexpr int kSlotBytes = 2 * kPlaneBytes;
+constexpr int kTxBytes = 2 * (kTileM + 2) * kRowBytes;
+constexpr int kTapBytesB = 128 * kRowBytes;                    // [Wh | Wl'] rows x 16 k
+constexpr int kWBytes = 9 * kTapBytesB;                        // 36 KB
+constexpr int kStageBytes = 2048;
+constexpr int kAccCols = 128;
+constexpr int kTmemCols = 256;
+constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
+
+struct Params {
+  const uint8_t* wimg;
+  const float* scale;
+  const float* bias;
+  int relu;
+  int NF, Hc, Wc;
+  int tiles_x, strips_y, strip_rows;
+  long long n_items;
+};
+struct Item { int nf, h0, w0, ntiles; };
+
+__device__ __forceinline__ Item decode(const Params& p, long long item) {
+  const int per_frame = p.tiles_x * p.strips_y;
+  Item it;
+  it.nf = (int)(item / per_frame);
+  const int rem = (int)(item - (long long)it.nf * per_frame);
+  const int sy = rem / p.tiles_x;
+  it.w0 = (rem - sy * p.tiles_x) * kTileM;
+  it.h0 = sy * p.strip_rows;
+  it.ntiles = min(p.strip_rows, p.Hc - it.h0);
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
+                     const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
+                     const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_s = smem;
+  uint8_t* a_s = w_s + kWBytes;
+  uint8_t* st_s = a_s + kSlots * kSlotBytes;
+  uint8_t* tail = st_s + 8 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0] w, full[S], empty[S], tfull[2], tempty[2]
+  float* aff_s = reinterpret_cast<float*>(tail + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlots + s]); };
+  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlots + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[3 + 2 * kSlots + b]); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int c = threadIdx.x - 64;
+    aff_s[c] = p.scale ? p.scale[c] : 1.f;
+    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(bar_w, kWBytes);
+      bulk_load_1d(smem_u32(w_s), p.wimg, kWBytes, bar_w);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode(p, item);
+        for (int q = 0; q < it.ntiles + 2; ++q) {
+          mbar_wait(bar_empty(slot), phase ^ 1);
+          mbar_arrive_expect_tx(bar_full(slot), kTxBytes);
+          const uint32_t dst = smem_u32(a_s + slot * kSlotBytes);
+          tma_load_4d(dst, &in_hi, bar_full(slot), 0, it.w0 - 1, it.h0 - 1 + q, it.nf);
+          tma_load_4d(dst + kPlaneBytes, &in_lo, bar_full(slot), 0, it.w0 - 1, it.h0 - 1 + q, it.nf);
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_main = make_idesc(kTileM, 128);
+      constexpr uint32_t idesc_lo = make_idesc(kTileM, 64);
+      mbar_wait(bar_w, 0);
+      const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
+      int first = 0;
+      uint32_t first_phase = 0;
+      int buf = 0;
+      uint32_t tphase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode(p, item);
+        int wait_slot = first;
+        uint32_t wait_phase = first_phase;
+        int rows_ready = 0;
+        for (int j = 0; j < it.ntiles; ++j) {
+          mbar_wait(bar_tempty(buf), tphase ^ 1);
+          while (rows_ready < j + 3) {
+            mbar_wait(bar_full(wait_slot), wait_phase);
+            if (++wait_slot == kSlots) { wait_slot = 0; wait_phase ^= 1; }
+            ++rows_ready;
+          }
+          tc_fence_after();
+          const uint32_t d_main = tmem_base + buf * kAccCols;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int slot = (first + j + ky) % kSlots;
+            const uint32_t a_row = a_base + slot * kSlotBytes;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int tap = ky * 3 + kx;
+              const uint64_t b_w = sdesc_sw32(w_base + tap * kTapBytesB);
+              umma_f16(d_main, sdesc_sw32(a_row + kx * kRowBytes), b_w, idesc_main, tap != 0);
+              umma_f16(d_main + 64, sdesc_sw32(a_row + kPlaneBytes + kx * kRowBytes), b_w, idesc_lo, 1u);
+            }
+          }
+          const int dead = (first + j) % kSlots;
+          umma_commit(bar_empty(dead));
+          if (j == it.ntiles - 1) {
+            umma_commit(bar_empty((dead + 1) % kSlots));
+            umma_commit(bar_empty((dead + 2) % kSlots));
+          }
+          umma_commit(bar_tfull(buf));
+          if (++buf == 2) { buf = 0; tphase ^= 1; }
+        }
+        first = wait_slot;
+        first_phase = wait_phase;
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int half = e >> 2;
+    const uint32_t stage = smem_u32(st_s + e * kStageBytes);
+    int buf = 0;
+    uint32_t tphase = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const Item it = decode(p, item);
+      for (int j = 0; j < it.ntiles; ++j) {
+        const int h = it.h0 + j;
+        mbar_wait(bar_tfull(buf), tphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
+        uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          uint32_t acc[16], cor[16];
+          tmem_ld16(t_row + half * 32 + part * 16, acc);
+          tmem_ld16(t_row + 64 + half * 32 + part * 16, cor);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int c = half * 32 + part * 16 + i + u;
+              float a = fmaf(__uint_as_float(cor[i + u]), kLoInvScale, __uint_as_float(acc[i + u]));
+              a = fmaf(a, aff_s[c], aff_s[64 + c]);
+              v[u] = p.relu ? fmaxf(a, 0.f) : a;
+            }
+            __half h0, l0, h1, l1;
+            split_f16(v[0], h0, l0);
+            split_f16(v[1], h1, l1);
+            hi_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(buf));
+        const uint32_t row_addr = stage + lane * 64;
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((q ^ sw) << 4)), "r"(pk[4 * q]),
+                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, it.w0 + quarter * 32, h, it.nf);
+            bulk_commit();
+          }
+        }
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tcf
+
+typedef CUresult (*PFN_encodeTiledF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* map, const __half* plane, int channels, int NF, int Hc, int Wc, int box_c, int box_w,
+                    CUtensorMapSwizzle sw) {
+  static PFN_encodeTiledF enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_encodeTiledF>(ptr);
+  }
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
+  const cuuint64_t rb = (cuuint64_t)channels * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
+  cuuint64_t strides[3] = {rb, (cuuint64_t)Wc * rb, (cuuint64_t)Hc * Wc * rb};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
+  return DEQSCI_OK;
+}
+
+size_t tcf_weight_image_bytes() { return tcf::kWBytes; }
+
+// w [64 cout][cin][3][3] fp32 (cin = 5 or 1) -> [tap][128 rows: hi(W) | lo'(W)][16 k] fp16, 32-byte swizzle
+// (16-byte chunk index XOR bit 2 of the row index); k >= cin is zero.
+void tcf_pack_weights(const float* w, int cin, uint8_t* img) {
+  memset(img, 0, tcf::kWBytes);
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    for (int n = 0; n < 128; ++n) {
+      const int co = n & 63;
+      for (int k = 0; k < cin; ++k) {
+        const float v = w[((co * cin + k) * 3 + ky) * 3 + kx];
+        const __half hi = __float2half_rn(v);
+        __half val = hi;
+        if (n >= 64) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
+        const size_t byte = (size_t)tap * tcf::kTapBytesB + (size_t)n * 32 + (size_t)(((k >> 3) ^ ((n >> 2) & 1)) << 4) +
+                            (size_t)(k & 7) * 2;
+        *reinterpret_cast<__half*>(img + byte) = val;
+      }
+    }
+  }
+}
+
+bool tcf_supported(int Wc) {
+  static const int enabled = getenv("DEQSCI_TC_FIRST") ? atoi(getenv("DEQSCI_TC_FIRST")) : 1;
+  return enabled && Wc > 64;
+}
+
+// planes_in: [2][NF,Hc,Wc,16] fp16 (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
+int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
+                         const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
+                         int Wc, cudaStream_t st) {
+  tcf::Params p;
+  p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
+  p.NF = NF; p.Hc = Hc; p.Wc = Wc;
+  p.tiles_x = (Wc + tcf::kTileM - 1) / tcf::kTileM;
+  int R = 16;
+  while (R > 2 && (long long)NF * p.tiles_x * ((Hc + R - 1) / R) < 6LL * num_sms()) R /= 2;
+  p.strip_rows = R;
+  p.strips_y = (Hc + R - 1) / R;
+  p.n_items = (long long)NF * p.tiles_x * p.strips_y;
+  CUtensorMap in_hi, in_lo, out_hi, out_lo;
+  int rc;
+  if ((rc = make_map(&in_hi, planes_in, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&in_lo, planes_in + in_plane_elems, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  const int grid = (int)(p.n_items < num_sms() ? p.n_items : num_sms());
+  DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   tcf::kSmemBytes));
+  ProfScope prof(PK_CONV_FIRST, st);
+  tcf::conv_first_tc_kernel<<<grid, tcf::kThreads, tcf::kSmemBytes, st>>>(in_hi, in_lo, out_hi, out_lo, p);
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+}  // namespace deqsci

@@ -177,3 +177,96 @@ extern "C" int deqsci_gap_vjp(const float* v, const float* phi, const float* phi
                               int B, int H, int W, int T, void* stream) {
   return launch_gap<OP_VJP>(v, nullptr, phi, phi_sum, add, out, B, H, W, T, stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Prologue of the tensor-core first conv layer: (optional) GAP step, then the frame-major,
+// channels-last 16-channel input planes that conv_tc_first.cu loads with TMA.
+//   FFDNet: one thread per half-resolution pixel (b,i,j): z' of its 2x2 fine pixels for all T frames,
+//           plane row [b*T+t, i, j, :] = {sigma, z'(0,0), z'(0,1), z'(1,0), z'(1,1), 0 x 11}
+//           (pixel-unshuffle + noise map of networks/ffdnet/functions.py:16-53; because sigma is a real
+//           channel, the conv's zero padding of the noise map is just TMA out-of-bounds fill)
+//   DnCNN : one thread per pixel, plane row = {z', 0 x 15}
+// Values are stored as fp16 pairs (hi plane, lo plane), like every activation of the stack.
+// Bytes per measurement (256x256x8): read z, Phi 4 MiB (+y, phi_sum), write z' 2 MiB + planes 8 MiB.
+// ------------------------------------------------------------------------------------------------
+namespace deqsci {
+
+template <int KIND>
+__global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                                       const float* __restrict__ phi,
+                                                       const float* __restrict__ phi_sum,
+                                                       float* __restrict__ zprime_out, __half* __restrict__ planes,
+                                                       long long plane_elems, float sigma, int B, int H, int W,
+                                                       int T, int do_gap) {
+  constexpr int SC = (KIND == DEQSCI_NET_FFDNET) ? 2 : 1;
+  constexpr int NSUB = SC * SC;
+  const int Hc = H / SC, Wc = W / SC;
+  const long long n = (long long)B * Hc * Wc;
+  __half s_hi, s_lo;
+  split_f16(sigma, s_hi, s_lo);
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < n;
+       id += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(id % Wc);
+    const int i = (int)((id / Wc) % Hc);
+    const int b = (int)(id / ((long long)Wc * Hc));
+    float r[NSUB];
+    long long pix[NSUB];
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+      pix[s] = ((long long)b * H + SC * i + s / SC) * W + SC * j + s % SC;
+      r[s] = 0.f;
+      if (do_gap) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = __fadd_rn(acc, __fmul_rn(z[pix[s] * T + t], phi[pix[s] * T + t]));
+        r[s] = __fdiv_rn(__fsub_rn(y[pix[s]], acc), phi_sum[pix[s]]);
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      __align__(16) __half hi[16];
+      __align__(16) __half lo[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { hi[c] = __float2half_rn(0.f); lo[c] = hi[c]; }
+      if (KIND == DEQSCI_NET_FFDNET) { hi[0] = s_hi; lo[0] = s_lo; }
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s) {
+        float v = z[pix[s] * T + t];
+        if (do_gap) {
+          v = __fadd_rn(v, __fmul_rn(r[s], phi[pix[s] * T + t]));
+          zprime_out[pix[s] * T + t] = v;
+        }
+        const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
+        split_f16(v, hi[c], lo[c]);
+      }
+      const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * 16;
+      uint4* dh = reinterpret_cast<uint4*>(planes + row);
+      uint4* dl = reinterpret_cast<uint4*>(planes + plane_elems + row);
+      dh[0] = reinterpret_cast<const uint4*>(hi)[0];
+      dh[1] = reinterpret_cast<const uint4*>(hi)[1];
+      dl[0] = reinterpret_cast<const uint4*>(lo)[0];
+      dl[1] = reinterpret_cast<const uint4*>(lo)[1];
+    }
+  }
+}
+
+// planes: [2][B*T, Hc, Wc, 16] fp16; plane_elems = B*T*Hc*Wc*16.  y/phi/phi_sum/zprime_out may be null
+// when do_gap == 0 (the planes are then built from z itself).
+int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
+                    float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
+                    int T, bool do_gap, cudaStream_t st) {
+  const int SC = kind == DEQSCI_NET_FFDNET ? 2 : 1;
+  const long long n = (long long)B * (H / SC) * (W / SC);
+  long long blocks = (n + 127) / 128;
+  const long long cap = (long long)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  ProfScope prof(PK_GAP, st);
+  if (kind == DEQSCI_NET_FFDNET)
+    gap_prep_kernel<DEQSCI_NET_FFDNET><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
+                                                                          plane_elems, sigma, B, H, W, T, do_gap);
+  else
+    gap_prep_kernel<DEQSCI_NET_DNCNN><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
+                                                                         plane_elems, sigma, B, H, W, T, do_gap);
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+}  // namespace deqsci
