@@ -87,7 +87,12 @@ class EquilibriumProxGradSCI(nn.Module):
         return self._autograd_forward(z, y, Phi, Phi_sum)
 
     def _autograd_forward(self, z, y, Phi, Phi_sum):
-        """Graph-attached evaluation for training (PyTorch autograd; not the inference hot path)."""
+        """Graph-attached evaluation for training (PyTorch autograd; not the inference hot path).
+        cuDNN's TF32 convolutions (PyTorch's default on Ampere+) put 1e-3..1e-2 errors on the
+        iterates and gradients, far outside the parity bar, so the library path is pinned to fp32."""
+        if z.is_cuda and torch.backends.cudnn.allow_tf32:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
         bsz, w, h, c = z.shape
         tag = self.nonlinear_op.tag
         fb = torch.sum(z * Phi, dim=3)

@@ -12,8 +12,10 @@ import ctypes
 import torch
 import torch.nn as nn
 
+from .. import ops
 from .._lib import DeqsciError, check, lib
 from ..ops import _req, _stream
+from ..utils import cg_utils
 
 MAX_M = 8
 
@@ -184,9 +186,20 @@ class DEQFixedPoint(nn.Module):
         z0 = z.clone().detach().requires_grad_()
         f0 = self.f(z0, x, Phi, Phi_sum)
 
+        # tag 'ffdnet': the denoiser sees x.data, so the Jacobian of f w.r.t. z is the GAP projector and
+        # the VJP is one fused kernel (deqsci_gap_vjp) instead of a trip through the autograd graph
+        native_vjp = (getattr(getattr(self.f, "nonlinear_op", None), "tag", None) == 'ffdnet' and z.is_cuda
+                      and getattr(self.f, "A", None) is cg_utils.A_torch_ and getattr(self.f, "At", None) is cg_utils.At_torch_)
+
         def backward_hook(grad):
-            g, self.backward_res = self.solver(
-                lambda v: torch.autograd.grad(f0, z0, v, retain_graph=True)[0] + grad, grad, **self.kwargs)
+            if native_vjp:
+                g0 = grad.contiguous()
+                vjp = lambda v, out=None: ops.gap_vjp(v, Phi, Phi_sum, add=g0, out=out)
+                vjp.supports_out = True
+            else:
+                vjp = lambda v: torch.autograd.grad(f0, z0, v, retain_graph=True)[0] + grad
+            with torch.no_grad():
+                g, self.backward_res = self.solver(vjp, grad, **self.kwargs)
             return g
 
         z.register_hook(backward_hook)

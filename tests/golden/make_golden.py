@@ -177,9 +177,47 @@ def stage_full(denoisers, scenes):
                 np.savez_compressed(path, **out)
 
 
+def stage_train():
+    """One implicit-differentiation training step (reference training/sci_equilibrium_training.py:54-75)
+    on a 32x32x8 crop, B=2, max_iter=12, denoiser in train mode: loss and parameter gradients."""
+    ref_import.install_shims()
+    from utils.cg_utils import A_torch_, At_torch_
+    gt, mask, meas = load_scene_ref("traffic")
+    C = (slice(100, 132), slice(110, 142))
+    gt_c = torch.from_numpy(np.stack([gt[C][..., 0:8], gt[C][..., 16:24]]))
+    Phi_c = torch.from_numpy(np.stack([mask[C], mask[C]]))
+    y_c = A_torch_(gt_c, Phi_c)
+    Phi_sum_c = torch.sum(Phi_c, axis=3)
+    Phi_sum_c[Phi_sum_c == 0] = 1
+    out = {"gt": gt_c.numpy(), "Phi": Phi_c.numpy(), "y": y_c.numpy()}
+    for d in DENOISERS:
+        solver, deq = ref_import.build_reference_deq(d, max_iter=12)
+        solver.train()
+        solver.nonlinear_op.train()
+        x0 = At_torch_(y_c, Phi_c)
+        rec = deq.forward(y_c, Phi_c, Phi_sum_c, initial_point=x0)
+        loss = torch.nn.MSELoss(reduction='mean')(rec, gt_c)
+        loss.backward()
+        out["loss_" + d] = np.array(float(loss))
+        out["fres_" + d] = np.array(deq.forward_res)
+        out["bres_" + d] = np.array(deq.backward_res)
+        out["rec_" + d] = rec.detach().numpy()
+        names, norms = [], []
+        for n_, p_ in solver.named_parameters():
+            if p_.grad is not None:
+                names.append(n_)
+                norms.append(float(p_.grad.norm()))
+                if p_.grad.numel() <= 4096:
+                    out["grad_%s::%s" % (d, n_)] = p_.grad.numpy().copy()
+        out["gradnames_" + d] = np.array(names)
+        out["gradnorms_" + d] = np.array(norms)
+        print(d, "loss", float(loss), "fres", deq.forward_res, "bres", deq.backward_res, "n grads", len(names))
+    np.savez_compressed(os.path.join(HERE, "train_vectors.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", required=True, choices=["assets", "small", "full"])
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train"])
     ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
     ap.add_argument("--scenes", nargs="*", default=SCENES)
     a = ap.parse_args()
@@ -188,5 +226,7 @@ if __name__ == "__main__":
         stage_assets()
     elif a.stage == "small":
         stage_small()
+    elif a.stage == "train":
+        stage_train()
     else:
         stage_full(a.denoisers, a.scenes)
