@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("DEQSCI_BENCH_BATCH", 16)),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("DEQSCI_BENCH_BATCH", 32)),
                     help="measurements per GPU per step")
     ap.add_argument("--precision", default="tc_split", choices=["tc_split", "fp32", "tc_single"])
     ap.add_argument("--sample-every", type=int, default=11, help="event-time every k-th kernel launch")

@@ -473,9 +473,12 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tc2::kTileM - 1) / tc2::kTileM;
   const int pairs_hw = num_sms() / 2;
-  // strip height: the largest power of two <= 16 dividing Hc that still leaves >= 6 pair-items per SM pair
+  // strip height: the largest power of two <= 16 dividing Hc that still leaves >= `rounds` strips per SM.
+  // Longer strips amortise the pipeline refill at strip boundaries (the 4-slot ring cannot prefetch the
+  // next strip's three start rows while the last tile still holds three slots)
   int R = 16;
-  while (R > 1 && (Hc % R != 0 || (long long)NF * p.tiles_x * (Hc / R) < 12LL * pairs_hw)) R /= 2;
+  static const int rounds = getenv("DEQSCI_TC_ROUNDS") ? atoi(getenv("DEQSCI_TC_ROUNDS")) : 6;
+  while (R > 1 && (Hc % R != 0 || (long long)NF * p.tiles_x * (Hc / R) < 2LL * rounds * pairs_hw)) R /= 2;
   p.strip_rows = R;
   p.strips_y = Hc / R;
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;

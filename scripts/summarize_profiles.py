@@ -49,7 +49,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic"]
 with open(os.path.join(OUT, "%s_kernel_metrics.md" % label), "w") as f:
     f.write("# ncu --set full --clock-control none captures (B = 8 measurements = 64 frames of 128x128 per launch)\n\n")
-    for kind in ["hidden", "last", "first", "gram", "mix"]:
+    for kind in ["hidden", "last", "first", "prep", "gram", "mix"]:
         rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (kind, tag))
         if not os.path.exists(rep):
             continue
