@@ -101,16 +101,20 @@ __global__ void __launch_bounds__(kGramThreads) anderson_gram_kernel(const float
   }
 }
 
-// Solves the bordered system H a = e0, H = [[0, 1^T],[1, GG + lam I]] of size (n+1), returns
+// Solves the bordered system H a = e0, H = [[0, 1^T],[1, GG + lam I]] of size S = n+1, returns
 // a[1..n] in alpha.  Right-looking LU with partial pivoting (first maximal |entry| wins, pivot
 // applied through its reciprocal as LAPACK's getf2 does), then forward/back substitution.
-__device__ void bordered_solve(const float* gram_b, int m, int n, float lam, float* alpha_out) {
-  float Hm[kMaxM + 1][kMaxM + 1];
-  float rhs[kMaxM + 1];
-  const int s = n + 1;
-  for (int i = 0; i < s; ++i) {
+// S is a compile-time constant so the matrix stays in registers (fully unrolled loops).
+template <int S>
+__device__ __forceinline__ void bordered_solve_fixed(const float* gram_b, int m, float lam, float* alpha_out) {
+  constexpr int n = S - 1;
+  float Hm[S][S];
+  float rhs[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
     rhs[i] = (i == 0) ? 1.f : 0.f;
-    for (int j = 0; j < s; ++j) {
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
       float v;
       if (i == 0 && j == 0) v = 0.f;
       else if (i == 0 || j == 0) v = 1.f;
@@ -118,36 +122,63 @@ __device__ void bordered_solve(const float* gram_b, int m, int n, float lam, flo
       Hm[i][j] = v;
     }
   }
-  for (int k = 0; k < s; ++k) {
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
     int p = k;
     float best = fabsf(Hm[k][k]);
-    for (int i = k + 1; i < s; ++i) {
+#pragma unroll
+    for (int i = k + 1; i < S; ++i) {
       const float v = fabsf(Hm[i][k]);
       if (v > best) { best = v; p = i; }
     }
-    if (p != k) {
-      for (int j = 0; j < s; ++j) { const float t = Hm[k][j]; Hm[k][j] = Hm[p][j]; Hm[p][j] = t; }
-      const float t = rhs[k]; rhs[k] = rhs[p]; rhs[p] = t;
+    // row swap k <-> p without dynamic register indexing
+#pragma unroll
+    for (int i = k + 1; i < S; ++i) {
+      if (i == p) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) { const float t = Hm[k][j]; Hm[k][j] = Hm[i][j]; Hm[i][j] = t; }
+        const float t = rhs[k]; rhs[k] = rhs[i]; rhs[i] = t;
+      }
     }
     const float rp = 1.0f / Hm[k][k];
-    for (int i = k + 1; i < s; ++i) {
+#pragma unroll
+    for (int i = k + 1; i < S; ++i) {
       const float l = Hm[i][k] * rp;
       Hm[i][k] = l;
-      for (int j = k + 1; j < s; ++j) Hm[i][j] = Hm[i][j] - l * Hm[k][j];
+#pragma unroll
+      for (int j = k + 1; j < S; ++j) Hm[i][j] = Hm[i][j] - l * Hm[k][j];
     }
   }
-  // L y = P b (unit lower), then U x = y
-  for (int i = 1; i < s; ++i) {
+#pragma unroll
+  for (int i = 1; i < S; ++i) {
     float v = rhs[i];
+#pragma unroll
     for (int j = 0; j < i; ++j) v -= Hm[i][j] * rhs[j];
     rhs[i] = v;
   }
-  for (int i = s - 1; i >= 0; --i) {
+#pragma unroll
+  for (int i = S - 1; i >= 0; --i) {
     float v = rhs[i];
-    for (int j = i + 1; j < s; ++j) v -= Hm[i][j] * rhs[j];
+#pragma unroll
+    for (int j = i + 1; j < S; ++j) v -= Hm[i][j] * rhs[j];
     rhs[i] = v / Hm[i][i];
   }
-  for (int j = 0; j < m; ++j) alpha_out[j] = (j < n) ? rhs[j + 1] : 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxM; ++j)
+    if (j < m) alpha_out[j] = (j < n) ? rhs[(j + 1 < S) ? j + 1 : 0] : 0.f;
+}
+
+__device__ void bordered_solve(const float* gram_b, int m, int n, float lam, float* alpha_out) {
+  switch (n) {
+    case 1: bordered_solve_fixed<2>(gram_b, m, lam, alpha_out); break;
+    case 2: bordered_solve_fixed<3>(gram_b, m, lam, alpha_out); break;
+    case 3: bordered_solve_fixed<4>(gram_b, m, lam, alpha_out); break;
+    case 4: bordered_solve_fixed<5>(gram_b, m, lam, alpha_out); break;
+    case 5: bordered_solve_fixed<6>(gram_b, m, lam, alpha_out); break;
+    case 6: bordered_solve_fixed<7>(gram_b, m, lam, alpha_out); break;
+    case 7: bordered_solve_fixed<8>(gram_b, m, lam, alpha_out); break;
+    default: bordered_solve_fixed<9>(gram_b, m, lam, alpha_out); break;
+  }
 }
 
 // One CTA; one warp per sample (looping), lane-parallel fp64 reduction over chunks.

@@ -44,6 +44,7 @@ class EquilibriumProxGradSCI(nn.Module):
         """Reference :409-413: `if self.y != y.mean(): reset else: sigma *= 0.971`.  The mean of a
         tensor we have already seen (same storage, same version) is not recomputed, so a solver
         loop costs one device sync per new measurement instead of one per call."""
+        self._undo = (self.y, self._sigma, self._y_key)      # state before this call (rollback_call)
         key = (y.data_ptr(), y._version, tuple(y.shape), str(y.device))
         if key != self._y_key:
             mean = float(y.mean())
@@ -54,6 +55,14 @@ class EquilibriumProxGradSCI(nn.Module):
                 return self._sigma
         self._sigma = np.float32(self._sigma * _DECAY)
         return self._sigma
+
+    def rollback_call(self):
+        """Undoes the schedule advance of the most recent forward() (a solver that queued one
+        speculative iteration past convergence calls this; the map has no other per-call state in
+        eval mode)."""
+        if self.nonlinear_op.tag == 'ffdnet' and getattr(self, "_undo", None) is not None:
+            self.y, self._sigma, self._y_key = self._undo
+            self._undo = None
 
     def skip_call(self):
         """Advances the sigma schedule as one forward() call would, without computing anything

@@ -77,6 +77,26 @@ class _AndersonState:
         return float(self.res_host[1]) / (eps + float(self.res_host[2]))
 
 
+class _ResidualRing:
+    """Residuals of every iteration land in pinned host memory through async 16-byte copies; an event
+    per iteration lets the host read iteration k-1's value while iteration k is already queued."""
+
+    def __init__(self, st, n):
+        self.st = st
+        self.host = torch.zeros((max(n, 1), 4), dtype=torch.float32).pin_memory()
+        self.events = {}
+
+    def push(self, k):
+        self.host[k].copy_(self.st.res_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.st.dev))
+        self.events[k] = ev
+
+    def get(self, k, eps):
+        self.events[k].synchronize()
+        return float(self.host[k, 1]) / (eps + float(self.host[k, 2]))
+
+
 def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
     x0 = _req(x0, "x0")
     st = _AndersonState(x0, m)
@@ -88,7 +108,13 @@ def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
     _call_f(f, st.slot(st.X, 1), st.slot(st.F, 1))
     st.update(0, 1, lam, eps)          # Gram entries of the two start-up slots
     st.update(1, 2, lam, eps)          # ... and alpha for k = 2
-    res_list, res, current_k = [], None, 0
+    # The reference tests `res < tol` after every iteration (two .item() syncs).  When the iterate map
+    # can undo a speculative call (rollback), iteration k is queued BEFORE iteration k-1's residual is
+    # read, so the device never idles on the host; results are identical (the slot returned on
+    # convergence, X[(k-1) % m], is not touched by iteration k).
+    lagged = getattr(f, "supports_rollback", False) and m >= 2
+    ring = _ResidualRing(st, max_iter)
+    current_k, stop_k = 0, None
     for k in range(2, max_iter):
         current_k = k
         n = min(k, m)
@@ -97,10 +123,18 @@ def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
         _call_f(f, st.slot(st.X, s), st.slot(st.F, s))
         # the same launch pair produces this iteration's residual and the next iteration's alpha
         st.update(s, min(k + 1, m), lam, eps)
-        res = st.fetch_res(eps)
-        res_list.append(res)
-        if res < tol:
+        ring.push(k)
+        if lagged:
+            if k > 2 and ring.get(k - 1, eps) < tol:
+                f.rollback()                       # iteration k was speculative
+                stop_k = current_k = k - 1
+                break
+        elif ring.get(k, eps) < tol:
+            stop_k = k
             break
+    last = stop_k if stop_k is not None else current_k
+    res_list = [ring.get(k, eps) for k in range(2, last + 1)] if last >= 2 else []
+    res = res_list[-1] if res_list else None
     out = st.slot(st.X, current_k % m).clone()
     return out, (res_list if keep_res else res)
 
@@ -145,6 +179,10 @@ class _BoundIterate:
     def __init__(self, f, x, Phi, Phi_sum):
         self.f, self.x, self.Phi, self.Phi_sum = f, x, Phi, Phi_sum
         self.supports_out = hasattr(f, "_native_ok")
+        self.supports_rollback = hasattr(f, "rollback_call")
+
+    def rollback(self):
+        self.f.rollback_call()
 
     def __call__(self, z, out=None):
         if out is not None and self.supports_out and self.f._native_ok(z):

@@ -1,0 +1,10 @@
+#!/bin/bash
+# compute-sanitizer over the CUDA-core kernels and one small tensor-core reconstruction
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/ -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 4 gpurun_out/pytest_gpu.log
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "gap_kernels or anderson_kernels or residual_kernel" > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool (cuda-core kernels) exit $?"
+  grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_$tool.log | tail -3
+done
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_smoke.log 2>&1; echo "memcheck smoke exit $?"
+grep -E "ERROR SUMMARY|smoke ok" gpurun_out/sanitizer_memcheck_smoke.log | tail -3

@@ -253,6 +253,62 @@ def test_anderson_kernels_vs_numpy(dev, B, N, m):
             st.X[nxt].copy_(keep)
 
 
+def test_anderson_nchw_entry_point(dev):
+    """`anderson` (reference :114-150): NCHW input, returns the list of residuals; same update as
+    andersonexp.  Checked on a contractive affine map against the numpy oracle."""
+    from deqsci_b200.solvers.new_equilibrium_utils_yaping import anderson
+    rng = np.random.default_rng(11)
+    x0 = rng.standard_normal((3, 2, 16, 24)).astype(np.float32)
+    bvec = rng.standard_normal(x0.shape).astype(np.float32)
+    fm_t = lambda q: 0.6 * torch.roll(q, 1, dims=3) + t(bvec, dev)
+    z, res = anderson(fm_t, t(x0, dev), m=4, lam=1e-4, max_iter=14, tol=1e-9, beta=0.9)
+    fm_n = lambda q: (np.float32(0.6) * np.roll(q, 1, axis=3) + bvec).astype(np.float32)
+    trace = []
+    zo, reso = orc.andersonexp(fm_n, x0, m=4, lam=1e-4, max_iter=14, tol=1e-9, beta=0.9, trace=trace)
+    assert isinstance(res, list) and len(res) == 12
+    assert rel_l2(z.cpu().numpy(), zo) <= 1e-3
+    assert abs(res[-1] - reso) <= 0.05 * reso + 1e-7
+
+
+def test_early_stop_lagged_equals_synchronous(dev):
+    """tol reached mid-run: the lagged residual check (one speculative iteration, then rollback) returns
+    the same iterate, residual and effective call count as the per-iteration check and as the oracle."""
+    from deqsci_b200.solvers.new_equilibrium_utils_yaping import andersonexp
+    rng = np.random.default_rng(5)
+    x0 = rng.standard_normal((2, 8, 8, 8)).astype(np.float32)
+    bvec = rng.standard_normal(x0.shape).astype(np.float32)
+    bt = t(bvec, dev)
+
+    class Map:
+        supports_rollback = True
+
+        def __init__(self):
+            self.calls = 0
+
+        def __call__(self, q):
+            self.calls += 1
+            return 0.5 * torch.flip(q, dims=[2]) + bt
+
+        def rollback(self):
+            self.calls -= 1
+
+    lag = Map()
+    z1, r1 = andersonexp(lag, t(x0, dev), m=5, lam=1e-6, max_iter=40, tol=1e-4, beta=1.0)
+    calls = [0]
+
+    def plain(q):
+        calls[0] += 1
+        return 0.5 * torch.flip(q, dims=[2]) + bt
+    z2, r2 = andersonexp(plain, t(x0, dev), m=5, lam=1e-6, max_iter=40, tol=1e-4, beta=1.0)
+    assert lag.calls == calls[0] < 40 and r1 == r2 and r1 < 1e-4
+    assert torch.equal(z1, z2)
+    n_o = [0]
+    fo = lambda q: (n_o.__setitem__(0, n_o[0] + 1), (np.float32(0.5) * np.flip(q, axis=2) + bvec).astype(np.float32))[1]
+    zo, ro = orc.andersonexp(fo, x0, m=5, lam=1e-6, max_iter=40, tol=1e-4, beta=1.0)
+    assert n_o[0] == calls[0]
+    assert rel_l2(z1.cpu().numpy(), zo) <= 1e-4
+
+
 def test_residual_kernel(dev):
     from deqsci_b200.solvers.new_equilibrium_utils_yaping import forward_iteration
     a = torch.randn(3, 16, 16, 8, device=dev)
