@@ -42,6 +42,12 @@ bool tcf_supported(int Wc);
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
                          int Wc, cudaStream_t st);
+size_t tcl_weight_image_bytes();
+void tcl_pack_weights(const float* w, int cout, uint8_t* img);
+bool tcl_supported(int Wc);
+int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, const uint8_t* wimg,
+                        const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
+                        const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
 size_t tc2_weight_image_bytes();
 void tc2_pack_weights(const float* w, uint8_t* img);
 bool tc2_supported(int Hc, int Wc);
@@ -55,7 +61,8 @@ struct Layer {
   int cin = 0, cout = 0, relu = 0;
   float* w_cc = nullptr;      // CUDA-core packing [9][cin][cout] fp32
   uint8_t* w_tc = nullptr;    // tcgen05 shared-memory image (hidden and last layers, TC modes)
-  uint8_t* w_tc2 = nullptr;   // CTA-pair image (hidden layers, split precision)
+  uint8_t* w_tc2 = nullptr;   // second image: CTA-pair layout (hidden layers, split precision) or the
+                              // ky-transposed layout (last layer)
   float* scale = nullptr;     // [cout] or null
   float* bias = nullptr;      // [cout] or null
 };
@@ -147,7 +154,12 @@ extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layer
       std::vector<uint8_t> img(tc_weight_image_bytes(split, S.cout));
       tc_pack_weights(S.weight_host, S.cout, split, img.data());
       rc = upload(img.data(), img.size(), (void**)&L.w_tc);
-      if (rc == DEQSCI_OK && split && S.cout == kHidden) {
+      if (rc == DEQSCI_OK && i == num_layers - 1) {
+        std::vector<uint8_t> img2(tcl_weight_image_bytes());
+        tcl_pack_weights(S.weight_host, S.cout, img2.data());
+        rc = upload(img2.data(), img2.size(), (void**)&L.w_tc2);
+      }
+      if (rc == DEQSCI_OK && split && S.cout == kHidden && i < num_layers - 1) {
         std::vector<uint8_t> img2(tc2_weight_image_bytes());
         tc2_pack_weights(S.weight_host, img2.data());
         rc = upload(img2.data(), img2.size(), (void**)&L.w_tc2);
@@ -239,6 +251,9 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     cur ^= 1;
   }
   const Layer& LL = h->layers[nl - 1];
+  if (h->precision != DEQSCI_PREC_FP32 && tcl_supported(g.Wc))
+    return conv_last_tc_launch(LL.cout, act[cur], g.plane_elems, LL.w_tc2, LL.scale, LL.bias, LL.relu, g.NF, g.Hc,
+                               g.Wc, fuse_gap ? zprime_ws : z, out, H, W, T, st);
   if (h->precision != DEQSCI_PREC_FP32)
     return conv_tc_launch(h->kind == DEQSCI_NET_FFDNET ? 1 : 2, h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], nullptr,
                           g.plane_elems, LL.w_tc, LL.scale, LL.bias, LL.relu, g.NF, g.Hc, g.Wc,
