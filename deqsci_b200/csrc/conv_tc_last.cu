@@ -176,29 +176,31 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
       const int b = it.nf / p.T, t = it.nf - b * p.T;
       int rows_ready = 0;
       for (int j = 0; j < it.ntiles; ++j) {
+        // z' for this output row does not depend on the MMAs: issue the loads before waiting on them
+        const int h = it.h0 + j;
+        long long gidx[COUT];
+        float zp[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if (COUT == 4) gidx[c] = (((long long)b * p.H + 2 * h + (c >> 1)) * p.W + 2 * w + (c & 1)) * p.T + t;
+          else           gidx[c] = (((long long)b * p.H + h) * p.W + w) * p.T + t;
+          zp[c] = (w < p.Wc) ? __ldg(p.zprime + gidx[c]) : 0.f;
+        }
         while (rows_ready < j + 3) {
           const uint32_t g = g0 + rows_ready;
           mbar_wait(bar_tfull(g % kBufs), (g / kBufs) & 1);
           ++rows_ready;
         }
         tc_fence_after();
-        float noise[COUT];
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) noise[c] = 0.f;
+        uint32_t acc[3][4], cor[3][4];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const uint32_t t_addr = lane_base + ((g0 + j + ky) % kBufs) * kBufCols;
-          uint32_t acc[4], cor[4];
           const int col = (COUT == 4) ? 4 * ky : 0;              // COUT == 1: columns 0,1,2 sit in one x4 load
-          tmem_ld4(t_addr + col, acc);
-          tmem_ld4(t_addr + 16 + col, cor);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) {
-            const int e = (COUT == 4) ? c : ky;
-            noise[c] += fmaf(__uint_as_float(cor[e]), kLoInvScale, __uint_as_float(acc[e]));
-          }
+          tmem_ld4(t_addr + col, acc[ky]);
+          tmem_ld4(t_addr + 16 + col, cor[ky]);
         }
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -208,16 +210,18 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
             mbar_arrive(bar_tempty((g0 + j + 2) % kBufs));
           }
         }
-        const int h = it.h0 + j;
         if (w < p.Wc) {
 #pragma unroll
           for (int c = 0; c < COUT; ++c) {
-            float a = fmaf(noise[c], aff_s[c], aff_s[4 + c]);
+            float noise = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int e = (COUT == 4) ? c : ky;
+              noise += fmaf(__uint_as_float(cor[ky][e]), kLoInvScale, __uint_as_float(acc[ky][e]));
+            }
+            float a = fmaf(noise, aff_s[c], aff_s[4 + c]);
             if (p.relu) a = fmaxf(a, 0.f);
-            long long gidx;
-            if (COUT == 4) gidx = (((long long)b * p.H + 2 * h + (c >> 1)) * p.W + 2 * w + (c & 1)) * p.T + t;
-            else           gidx = (((long long)b * p.H + h) * p.W + w) * p.T + t;
-            p.out_cube[gidx] = __fsub_rn(p.zprime[gidx], a);
+            p.out_cube[gidx[c]] = __fsub_rn(zp[c], a);
           }
         }
       }
