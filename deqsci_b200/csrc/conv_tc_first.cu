@@ -30,7 +30,7 @@ constexpr int kSlotBytes = 2 * kPlaneBytes;
 constexpr int kTxBytes = 2 * (kTileM + 2) * kRowBytes;
 constexpr int kTapBytesB = 128 * kRowBytes;                    // [Wh | Wl'] rows x 16 k
 constexpr int kWBytes = 9 * kTapBytesB;                        // 36 KB
-constexpr int kStageBytes = 2048;
+constexpr int kStageBytes = 4096;                              // per epilogue warp: hi and lo staging, 32 px x 32 ch each
 constexpr int kAccCols = 128;
 constexpr int kTmemCols = 256;
 constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
@@ -206,23 +206,24 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
         if (lane == 0) mbar_arrive(bar_tempty(buf));
         const uint32_t row_addr = stage + lane * 64;
         const int sw = (lane >> 1) & 3;
+        if (lane == 0) bulk_wait_read0();          // the previous tile's two stores have read the staging buffers
+        __syncwarp();
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((q ^ sw) << 4)), "r"(pk[4 * q]),
-                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + plane * 2048 + ((q ^ sw) << 4)),
+                         "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                          : "memory");
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, it.w0 + quarter * 32, h, it.nf);
-            bulk_commit();
-          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&out_hi, stage, half * 32, it.w0 + quarter * 32, h, it.nf);
+          tma_store_4d(&out_lo, stage + 2048, half * 32, it.w0 + quarter * 32, h, it.nf);
+          bulk_commit();
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
