@@ -65,7 +65,9 @@ __device__ __forceinline__ void cluster_sync() {
 }
 // arrive on a barrier anywhere in the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (release at CTA scope): the TMEM reads it orders were already fenced with
+  // tcgen05.fence::before_thread_sync; a .release.cluster here costs a GPU-scope MEMBAR + ERRBAR per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA row load into THIS CTA's shared memory, completing on `cluster_bar` (the leader's full barrier)
 __device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
@@ -112,6 +114,7 @@ struct Params {
   int tiles_x, strips_y, strip_rows;
   long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
   long long n_pair_items;
+  int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): epilogue computes but does not store
 };
 
 struct Strip { int nf, h0, w0; bool real; };
@@ -299,6 +302,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
         // stage (64-byte swizzle: chunk ^= (row >> 1) & 3) and store the two planes with TMA
         const uint32_t row_addr = stage + lane * 64;
         const int sw = (lane >> 1) & 3;
+        if (p.debug_skip_store) { if (++buf == 2) { buf = 0; tphase ^= 1; } continue; }
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
@@ -409,6 +413,8 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.strips_y = Hc / R;
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;
   p.n_pair_items = (p.n_strips + 1) / 2;
+  static const int skip_store = getenv("DEQSCI_TC_DEBUG_SKIP_STORE") ? atoi(getenv("DEQSCI_TC_DEBUG_SKIP_STORE")) : 0;
+  p.debug_skip_store = skip_store;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
   int rc;
   if ((rc = make_plane_map(&in_hi, act_in, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
