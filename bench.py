@@ -276,13 +276,15 @@ def run_gpu_arm(args, rank, world, local_rank):
         "metric": "DE-GAP-FFDnet reconstructions/s (256x256x8, 180 Anderson iterations)",
         "value": value, "unit": "recon/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 state; hidden convs fp16 hi/lo split operands, fp32 accumulate" if args.precision == "tc_split"
-                 else args.precision,
+        "dtype": "f32",
         "data": "synthetic (U[0,1) frames, Bernoulli(0.5) masks, independent per measurement); FFDNet weights = "
                 "reference net_gray.pth stand-in for the missing ffdnet.ckpt",
         "config": {"workload": "batch-sharded DE-GAP-FFDnet, 256x256x8, and_maxiters=180, m=5, beta=1, lam=1e-2 "
                                "(BASELINE.json configs[3])",
                    "batch_per_gpu": B, "measurements_per_step": world * B, "precision": args.precision,
+                   "arithmetic": "fp32 state and accumulation; conv operands split into fp16 hi + fp16 lo*2^11 "
+                                 "(3 tensor-core products, ~22 mantissa bits)" if args.precision == "tc_split"
+                                 else args.precision,
                    "f_calls_per_recon": F_CALLS, "anderson_updates_per_recon": AND_UPDATES,
                    "l2_policy": "working set per step (%.1f GB/GPU) exceeds the 126 MB L2" % (
                        B * (3 * M_HIST * H * W * T * 4 + 2 * 2 * (H // 2) * (W // 2) * T * 64 * 2) / 1e9),
@@ -302,6 +304,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "peak_source": peak_src + ", bf16 dense sustained",
                      "avg_launch_ms": hid_ms, "algorithmic_flop_per_launch": flop_per_launch,
                      "issued_mma_flop_factor": 3 if args.precision == "tc_split" else 1,
+                     "frac_issued": (3 if args.precision == "tc_split" else 1) * achieved / peak if peak else None,
                      "sampled_launches": int(n_samp[2])},
         "kernels": shares,
         "check": {"finite": finite, "psnr_vs_synthetic_gt_db": psnr},

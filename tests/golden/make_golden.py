@@ -177,6 +177,30 @@ def stage_full(denoisers, scenes):
                 np.savez_compressed(path, **out)
 
 
+def stage_dncnn_bn():
+    """models.DnCNN (the BatchNorm DnCNN behind `--denoiser DnCNN`) with 5 layers, seeded random
+    weights and BatchNorm statistics, eval mode: weights + output on a [2,1,40,72] input."""
+    ref_import.install_shims()
+    from networks.provable.model.models import DnCNN
+    torch.manual_seed(7)
+    net = DnCNN(channels=1, num_of_layers=5, tag='denoiser')
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    net.eval()
+    x = torch.rand(2, 1, 40, 72)
+    with torch.no_grad():
+        y = net(x)
+    out = {"x": x.numpy(), "y": y.numpy()}
+    for k, v in net.state_dict().items():
+        out["sd::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "dncnn_bn_vectors.npz"), **out)
+    print("dncnn_bn", y.shape, float(y.abs().max()))
+
+
 def stage_train():
     """One implicit-differentiation training step (reference training/sci_equilibrium_training.py:54-75)
     on a 32x32x8 crop, B=2, max_iter=12, denoiser in train mode: loss and parameter gradients."""
@@ -217,7 +241,7 @@ def stage_train():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train"])
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "dncnn_bn"])
     ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
     ap.add_argument("--scenes", nargs="*", default=SCENES)
     a = ap.parse_args()
@@ -228,5 +252,7 @@ if __name__ == "__main__":
         stage_small()
     elif a.stage == "train":
         stage_train()
+    elif a.stage == "dncnn_bn":
+        stage_dncnn_bn()
     else:
         stage_full(a.denoisers, a.scenes)

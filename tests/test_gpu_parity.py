@@ -470,3 +470,29 @@ def test_solver_sci_all_scenes_vs_reference(dev, full_recon, d):
             report.append((scene, fi, round(dp, 4), round(ds, 5)))
             assert abs(dp) <= tol_p and abs(ds) <= tol_s, report
     print("dPSNR/dSSIM vs reference:", report)
+
+
+# ---------------------------------------------------------------------------------------------
+# (7) the BatchNorm DnCNN behind `--denoiser DnCNN` (reference networks/provable/model/models.py)
+# ---------------------------------------------------------------------------------------------
+def test_dncnn_batchnorm_variant(dev):
+    from conftest import GOLDEN
+    from deqsci_b200.networks.provable.model.models import DnCNN
+    v = dict(np.load(os.path.join(GOLDEN, "dncnn_bn_vectors.npz")))
+    net = DnCNN(channels=1, num_of_layers=5).eval()
+    net.load_state_dict({k[len("sd::"):]: torch.from_numpy(v[k]) for k in v if k.startswith("sd::")}, strict=True)
+    net = net.to(dev)
+    got = net(t(v["x"], dev)).cpu().numpy()                     # narrow image: per-tap tensor-core path
+    assert rel_l2(got, v["y"]) <= 2e-5
+    # 17 layers on a wide image (CTA-pair hidden layers): vs the numpy oracle on random weights
+    torch.manual_seed(3)
+    big = DnCNN(channels=1, num_of_layers=17).eval()
+    for m in big.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.3)
+    sd = {k: p.detach().numpy() for k, p in big.state_dict().items()}
+    x = np.random.default_rng(1).random((2, 1, 24, 136)).astype(np.float32)
+    want = orc.dncnn_forward(x, sd, num_of_layers=17)
+    got = big.to(dev)(t(x, dev)).cpu().numpy()
+    assert rel_l2(got, want) <= 5e-5

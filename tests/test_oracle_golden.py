@@ -82,3 +82,13 @@ def test_synthetic_sharding_invariance():
     b = orc.synthetic_measurements(5, 1, H=8, W=8)
     np.testing.assert_array_equal(a["y"][2], b["y"][0])
     np.testing.assert_array_equal(a["Phi"][2], b["Phi"][0])
+
+
+def test_dncnn_batchnorm_variant():
+    """models.DnCNN (BatchNorm DnCNN, `--denoiser DnCNN`): oracle vs the reference module's output."""
+    import os
+    from conftest import GOLDEN
+    v = dict(np.load(os.path.join(GOLDEN, "dncnn_bn_vectors.npz")))
+    sd = {k[len("sd::"):]: v[k] for k in v if k.startswith("sd::")}
+    got = orc.dncnn_forward(v["x"], sd, num_of_layers=5)
+    assert rel_l2(got, v["y"]) <= 2e-6
