@@ -407,7 +407,16 @@ def test_full_scene_psnr_vs_reference(dev, full_recon, d, scene):
     Ps = Phi_sum_(Phi)
     max_iter = 180 if d == "ffdnet" else 100
     deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=max_iter, tol=1e-5)
+    seen = []
+    hk = solver.register_forward_pre_hook(lambda mod, args: seen.append(args[0].detach()[0, 96:160, 96:160].clone()))
     z = deq.forward(y, Phi, Ps, initial_point=At_torch_(y, Phi), train_flag=False)
+    hk.remove()
+    # per-iterate parity at full size: inputs of calls 2, 20 and the last solver call vs the reference's
+    # (64x64x8 crops of the 256x256x8 iterates), and the norm of every iterate
+    ncalls = int(full_recon[key + "_ncalls"])
+    assert len(seen) == ncalls - 1                     # the reference's extra call is skipped at inference
+    for k in (2, 20, ncalls - 2):
+        assert rel_l2(seen[k].cpu().numpy(), full_recon[key + "_in%d_crop" % k]) <= 1e-3, k
     rec = z.clip(0, 1).cpu().numpy()
     g = gt[None, :, :, 0:8]
     psnr = orc.psnr(g, rec)
