@@ -166,19 +166,22 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def build_deq(dev, precision):
-    from deqsci_b200.networks.ffdnet.models import FFDNet
+def build_deq(dev, precision, denoiser="ffdnet", max_iter=MAX_ITER):
     from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq_utils
     from deqsci_b200.solvers.equilibrium_solvers_yaping import EquilibriumProxGradSCI
     from deqsci_b200.utils.cg_utils import A_torch_, At_torch_
-    net = FFDNet(num_input_channels=1, tag="ffdnet")
+    from deqsci_b200.video_sci_proxgrad import build_denoiser
+    net = build_denoiser(denoiser)
     net.precision = precision
     net.eval()
     solver = EquilibriumProxGradSCI(A=A_torch_, At=At_torch_, nonlinear_operator=net, eta=0.2)
-    sd = {k: torch.from_numpy(v) for k, v in load_ffdnet_weights().items()}
+    wfile = {"ffdnet": "weights_ffdnet_gray.npz", "SimpleCNN": "weights_cnn.npz",
+             "RealSN_SimpleCNN": "weights_rsn_cnn.npz"}[denoiser]
+    d = np.load(os.path.join(ROOT, "tests", "golden", wfile))
+    sd = {k: torch.from_numpy(d[k]) for k in d.files if not k.startswith("shape::")}
     solver.load_state_dict(sd, strict=False)
     solver = solver.to(dev)
-    deq = eq_utils.DEQFixedPoint(solver, eq_utils.andersonexp, m=M_HIST, beta=1.0, lam=1e-2, max_iter=MAX_ITER,
+    deq = eq_utils.DEQFixedPoint(solver, eq_utils.andersonexp, m=M_HIST, beta=1.0, lam=1e-2, max_iter=max_iter,
                                  tol=1e-5)
     return solver, deq
 
@@ -198,7 +201,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch
-    solver, deq = build_deq(dev, args.precision)
+    solver, deq = build_deq(dev, args.precision, args.denoiser, args.max_iter)
     from deqsci_b200.distributed import shard_range
     lo, hi = shard_range(world * B, rank, world)      # contiguous index range per rank, no collective
     y_h, phi_h, gt = synthetic_batch(lo, hi - lo)
@@ -264,7 +267,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         return
     peaks, peak_src = measured_peaks()
     hid_ms = ms_sum[2] / max(n_samp[2], 1)
-    flop_per_launch = HIDDEN_FLOP_PER_LAUNCH_PER_MEAS * B
+    res_div = 2 if args.denoiser == "ffdnet" else 1              # FFDNet convs run at half resolution
+    flop_per_launch = 2 * 9 * 64 * 64 * (H // res_div) * (W // res_div) * T * B
     achieved = flop_per_launch / (hid_ms * 1e-3) / 1e12 if hid_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     kinds = ["gap", "conv_first", "conv_hidden", "conv_last", "anderson_gram", "anderson_solve", "anderson_mix"]
@@ -273,7 +277,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "est_ms_per_step": (ms_sum[i] / n_samp[i] * n_launch[i] / args.steps) if n_samp[i] else None}
               for i in range(k)}
     line = {
-        "metric": "DE-GAP-FFDnet reconstructions/s (256x256x8, 180 Anderson iterations)",
+        "metric": "DE-GAP-FFDnet reconstructions/s (256x256x8, 180 Anderson iterations)" if args.denoiser == "ffdnet"
+                  else "DE-GAP-%s reconstructions/s (256x256x8, %d Anderson iterations)" % (args.denoiser, args.max_iter),
         "value": value, "unit": "recon/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32",
@@ -285,7 +290,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "arithmetic": "fp32 state and accumulation; conv operands split into fp16 hi + fp16 lo*2^11 "
                                  "(3 tensor-core products, ~22 mantissa bits)" if args.precision == "tc_split"
                                  else args.precision,
-                   "f_calls_per_recon": F_CALLS, "anderson_updates_per_recon": AND_UPDATES,
+                   "f_calls_per_recon": args.max_iter + 1, "anderson_updates_per_recon": args.max_iter - 2,
                    "l2_policy": "working set per step (%.1f GB/GPU) exceeds the 126 MB L2" % (
                        B * (3 * M_HIST * H * W * T * 4 + 2 * 2 * (H // 2) * (W // 2) * T * 64 * 2) / 1e9),
                    "parallelism": "measurements sharded over ranks, no collective"},
@@ -299,7 +304,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      # dram read+write per launch from the ncu --set full capture in profiles/ (B=8: 497.8 MB)
-                     "traffic": 497.8e6 / 8 * B if args.precision == "tc_split" else None,
+                     "traffic": 497.8e6 / 8 * B if (args.precision == "tc_split" and args.denoiser == "ffdnet") else None,
                      "traffic_unit": "bytes per launch (profiles/r01_kernel_metrics.md, scaled by batch)",
                      "peak_source": peak_src + ", bf16 dense sustained",
                      "avg_launch_ms": hid_ms, "algorithmic_flop_per_launch": flop_per_launch,
@@ -309,7 +314,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "kernels": shares,
         "check": {"finite": finite, "psnr_vs_synthetic_gt_db": psnr},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.denoiser == "ffdnet":
         v, dt, per_call = cpu_port_recon_per_s(args.cpu_iters, y_h, phi_h)
         line["cpu_baseline"] = {"value": v, "unit": "recon/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "%d of %d iterate-map evaluations (+ Anderson updates) of one measurement, "
@@ -330,8 +335,13 @@ def main():
     ap.add_argument("--sample-every", type=int, default=11, help="event-time every k-th kernel launch")
     ap.add_argument("--cpu-iters", type=int, default=12, help="iterations of the CPU port sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--denoiser", default="ffdnet", choices=["ffdnet", "SimpleCNN", "RealSN_SimpleCNN"],
+                    help="side benchmarks (config 3); the headline metric is ffdnet")
+    ap.add_argument("--max-iter", type=int, default=None, help="and_maxiters (default 180 ffdnet, 100 otherwise)")
     args = ap.parse_args()
 
+    if args.max_iter is None:
+        args.max_iter = MAX_ITER if args.denoiser == "ffdnet" else 100
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
