@@ -114,7 +114,9 @@ struct Params {
   int tiles_x, strips_y, strip_rows;
   long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
   long long n_pair_items;
-  int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): epilogue computes but does not store
+  int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
+  __half* dbg_out_hi;
+  __half* dbg_out_lo;
 };
 
 struct Strip { int nf, h0, w0; bool real; };
@@ -302,7 +304,22 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
         // stage (64-byte swizzle: chunk ^= (row >> 1) & 3) and store the two planes with TMA
         const uint32_t row_addr = stage + lane * 64;
         const int sw = (lane >> 1) & 3;
-        if (p.debug_skip_store) { if (++buf == 2) { buf = 0; tphase ^= 1; } continue; }
+        if (p.debug_skip_store == 1) { if (++buf == 2) { buf = 0; tphase ^= 1; } continue; }
+        if (p.debug_skip_store == 2) {             // experiment: direct global stores, no smem staging
+          const int wpx = s.w0 + quarter * 32 + lane;
+          if (s.real && wpx < p.Wc) {
+            const long long off = (((long long)s.nf * p.Hc + h) * p.Wc + wpx) * 64 + half * 32;
+            uint4* dh = reinterpret_cast<uint4*>(p.dbg_out_hi + off);
+            uint4* dl = reinterpret_cast<uint4*>(p.dbg_out_lo + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dh[q] = make_uint4(hi_pk[4 * q], hi_pk[4 * q + 1], hi_pk[4 * q + 2], hi_pk[4 * q + 3]);
+              dl[q] = make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
+            }
+          }
+          if (++buf == 2) { buf = 0; tphase ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
@@ -415,6 +432,8 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.n_pair_items = (p.n_strips + 1) / 2;
   static const int skip_store = getenv("DEQSCI_TC_DEBUG_SKIP_STORE") ? atoi(getenv("DEQSCI_TC_DEBUG_SKIP_STORE")) : 0;
   p.debug_skip_store = skip_store;
+  p.dbg_out_hi = act_out;
+  p.dbg_out_lo = act_out + plane_elems;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
   int rc;
   if ((rc = make_plane_map(&in_hi, act_in, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;

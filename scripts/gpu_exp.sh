@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 0 1; do
+for v in ${@:-0 1}; do
   DEQSCI_TC_DEBUG_SKIP_STORE=$v timeout 600 python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline > gpurun_out/exp_$v.log 2>&1
   python - <<PY
 import json
