@@ -16,6 +16,17 @@ class DeqsciError(RuntimeError):
     pass
 
 
+class SolverOpts(Structure):
+    _fields_ = [("m", c_int), ("lam", c_float), ("beta", c_float), ("max_iter", c_int), ("tol", c_float),
+                ("sigma0", c_float), ("sigma_decay", c_float), ("sigma_start_call", c_int),
+                ("final_call", c_int), ("res_eps", ctypes.c_double)]
+
+
+class SolverResult(Structure):
+    _fields_ = [("residual", ctypes.c_double), ("iterations", c_int), ("f_calls", c_int), ("converged", c_int),
+                ("sigma_next", c_float)]
+
+
 class ConvLayer(Structure):
     _fields_ = [("cin", c_int), ("cout", c_int), ("relu", c_int),
                 ("weight_host", POINTER(c_float)), ("scale_host", POINTER(c_float)),
@@ -42,6 +53,9 @@ SIGNATURES = {
                                        c_float, c_float, _P]),
     "deqsci_anderson_mix": (c_int, [_P, _P, _P, c_int, c_int, c_longlong, c_int, c_int, c_float, _P]),
     "deqsci_residual": (c_int, [_P, _P, _P, _P, c_longlong, c_float, _P]),
+    "deqsci_reconstruct_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int, c_int]),
+    "deqsci_reconstruct": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
+                                   c_int, c_int, c_int, c_int, _P]),
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),

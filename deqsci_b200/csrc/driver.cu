@@ -1,0 +1,144 @@
+// Device-resident driver: one C-ABI call runs a whole DE-GAP reconstruction of a batch --
+// x0 = At(y), andersonexp(f, x0) (solvers/new_equilibrium_utils_yaping.py:153-189), then the final
+// f call that DEQFixedPoint.forward returns (:268) -- by queueing the library's own kernels from a
+// C++ loop.  No per-iteration host round trip stalls the device: every iteration's residual lands in
+// pinned host memory through a 16-byte async copy + event, and the host tests iteration k-1 while
+// iteration k is already queued (rolling back one speculative sigma step on convergence).
+#include <vector>
+
+#include "common.cuh"
+
+using namespace deqsci;
+
+namespace {
+size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  size_t hist_floats, gram_floats, alpha_floats, scratch_floats, floats_total;
+  size_t den_bytes, total_bytes;
+};
+
+Layout layout(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
+  Layout L;
+  const size_t N = (size_t)H * W * T;
+  L.hist_floats = (size_t)3 * m * B * N;
+  L.gram_floats = align_up_sz((size_t)B * m * m, 64);
+  L.alpha_floats = align_up_sz((size_t)B * m, 64);
+  L.scratch_floats = align_up_sz(deqsci_anderson_scratch_floats(B, m, (long long)N), 64);
+  L.floats_total = L.hist_floats + L.gram_floats + L.alpha_floats + L.scratch_floats + 64 /*res*/;
+  L.den_bytes = deqsci_denoiser_workspace_bytes(h, B, H, W, T);
+  L.total_bytes = 1024 + align_up_sz(L.floats_total * sizeof(float), 1024) + L.den_bytes;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
+  if (!h || B <= 0 || H <= 0 || W <= 0 || T <= 0 || m < 2 || m > 8) return 0;
+  Layout L = layout(h, B, H, W, T, m);
+  return L.den_bytes == 0 ? 0 : L.total_bytes;
+}
+
+extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+                                  const float* x0, float* out, const deqsci_solver_opts* o, void* workspace,
+                                  size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
+                                  void* stream) {
+  DEQSCI_CHECK_ARG(h && y && phi && phi_sum && out && o && workspace && result, "reconstruct: null pointer");
+  DEQSCI_CHECK_ARG(o->m >= 2 && o->m <= 8, "reconstruct: m=%d unsupported (2..8)", o->m);
+  DEQSCI_CHECK_ARG(o->max_iter >= 2, "reconstruct: max_iter=%d (need >= 2)", o->max_iter);
+  const size_t need = deqsci_reconstruct_workspace_bytes(h, B, H, W, T, o->m);
+  DEQSCI_CHECK_ARG(need != 0, "reconstruct: unsupported shape B=%d H=%d W=%d T=%d", B, H, W, T);
+  if (workspace_bytes < need) {
+    set_error("reconstruct: workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+    return DEQSCI_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = o->m;
+  const long long N = (long long)H * W * T;
+  const Layout L = layout(h, B, H, W, T, m);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up_sz(reinterpret_cast<uintptr_t>(workspace), 1024));
+  float* fl = reinterpret_cast<float*>(base);
+  float* X = fl;
+  float* F = X + (size_t)m * B * N;
+  float* G = F + (size_t)m * B * N;
+  float* gram = G + (size_t)m * B * N;
+  float* alpha = gram + L.gram_floats;
+  float* scratch = alpha + L.alpha_floats;
+  float* res_dev = scratch + L.scratch_floats;
+  void* den_ws = base + align_up_sz(L.floats_total * sizeof(float), 1024);
+  const size_t slot = (size_t)B * N;
+  auto Xs = [&](int s) { return X + (size_t)s * slot; };
+  auto Fs = [&](int s) { return F + (size_t)s * slot; };
+
+  // sigma schedule of tag 'ffdnet' (solvers/equilibrium_solvers_yaping.py:409-413): fp32 multiply per call
+  float sigma = o->sigma0, sigma_prev = o->sigma0;
+  for (int i = 0; i < o->sigma_start_call; ++i) sigma = sigma * o->sigma_decay;
+  int calls = 0;
+  auto f_call = [&](const float* zin, float* zout) -> int {
+    sigma_prev = sigma;
+    sigma = sigma * o->sigma_decay;
+    ++calls;
+    return deqsci_iterate(h, zin, y, phi, phi_sum, sigma_prev, zout, den_ws, L.den_bytes, B, H, W, T, stream);
+  };
+  auto undo_call = [&]() { sigma = sigma_prev; --calls; };   // a speculative iteration does not advance the schedule
+
+  int rc;
+  DEQSCI_CUDA(cudaMemsetAsync(gram, 0, (L.gram_floats + L.alpha_floats) * sizeof(float), st));
+  if (x0) DEQSCI_CUDA(cudaMemcpyAsync(Xs(0), x0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else if ((rc = deqsci_gap_adjoint(y, phi, Xs(0), B, H, W, T, stream))) return rc;      // initial_point = At(y)
+  if ((rc = f_call(Xs(0), Fs(0)))) return rc;
+  DEQSCI_CUDA(cudaMemcpyAsync(Xs(1), Fs(0), slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if ((rc = f_call(Xs(1), Fs(1)))) return rc;
+  if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, 0, 1, o->lam, (float)o->res_eps, stream))) return rc;
+  if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, 1, 2, o->lam, (float)o->res_eps, stream))) return rc;
+
+  // residual ring in pinned memory, one event per iteration
+  float* res_host = nullptr;
+  DEQSCI_CUDA(cudaMallocHost(&res_host, (size_t)o->max_iter * 4 * sizeof(float)));
+  std::vector<cudaEvent_t> ev(o->max_iter, nullptr);
+  auto res_of = [&](int k) -> double {
+    cudaEventSynchronize(ev[k]);
+    return (double)res_host[4 * k + 1] / (o->res_eps + (double)res_host[4 * k + 2]);
+  };
+  int current_k = 0, stop_k = -1;
+  rc = DEQSCI_OK;
+  for (int k = 2; k < o->max_iter && rc == DEQSCI_OK; ++k) {
+    current_k = k;
+    const int n = k < m ? k : m, s = k % m;
+    if ((rc = deqsci_anderson_mix(X, F, alpha, B, m, N, s, n, o->beta, stream))) break;
+    if ((rc = f_call(Xs(s), Fs(s)))) break;
+    if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, s, (k + 1 < m ? k + 1 : m),
+                                     o->lam, (float)o->res_eps, stream))) break;
+    if (cudaMemcpyAsync(res_host + 4 * k, res_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventRecord(ev[k], st) != cudaSuccess) {
+      set_error("reconstruct: residual copy / event failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = DEQSCI_ERR_CUDA;
+      break;
+    }
+    if (k > 2 && res_of(k - 1) < (double)o->tol) {      // iteration k was speculative
+      undo_call();
+      stop_k = current_k = k - 1;
+      break;
+    }
+  }
+  double res = 0.0;
+  if (rc == DEQSCI_OK && current_k >= 2) res = res_of(current_k);
+  if (rc == DEQSCI_OK) {
+    // z = f(z*): the reconstruction DEQFixedPoint.forward returns
+    if (o->final_call) rc = f_call(Xs(current_k % m), out);
+    else if (cudaMemcpyAsync(out, Xs(current_k % m), slot * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      rc = DEQSCI_ERR_CUDA;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);     // the pinned ring and events are released below
+  for (auto& v : ev) if (v) cudaEventDestroy(v);
+  cudaFreeHost(res_host);
+  if (rc != DEQSCI_OK) return rc;
+  if (e != cudaSuccess) { set_error("reconstruct: %s", cudaGetErrorString(e)); return DEQSCI_ERR_CUDA; }
+  result->residual = res;
+  result->iterations = current_k;
+  result->f_calls = calls;
+  result->converged = stop_k >= 0 ? 1 : 0;
+  result->sigma_next = sigma;
+  (void)stop_k;
+  return DEQSCI_OK;
+}

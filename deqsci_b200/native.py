@@ -67,6 +67,7 @@ class NativeDenoiser:
         self._h = handle
         self._fin = weakref.finalize(self, _destroy, handle)
         self._ws = None
+        self._rws = None
         self.num_layers = len(layers)
 
     def _workspace(self, B, H, W, T):
@@ -117,6 +118,36 @@ class NativeDenoiser:
                                        float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W, T,
                                        _stream(z)), "deqsci_iterate")
         return out
+
+    def reconstruct(self, y, phi, phi_sum, x0=None, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5,
+                    sigma_start_call=0, final_call=True, sigma0=60 / 255, sigma_decay=0.971):
+        """Whole DE-GAP reconstruction in ONE C-ABI call (deqsci_reconstruct): andersonexp on the
+        iterate map + the final f call.  Returns (out [B,H,W,T], SolverResult)."""
+        y = _req(y, "y", 3)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), y), _bcast_phi(_req(phi_sum, "Phi_sum", 3), y)
+        self._check_dev(y)
+        B, H, W, T = (int(s) for s in phi.shape)
+        if tuple(y.shape) != (B, H, W) or tuple(phi_sum.shape) != (B, H, W):
+            raise DeqsciError("reconstruct: inconsistent shapes y %s Phi %s Phi_sum %s" % (
+                tuple(y.shape), tuple(phi.shape), tuple(phi_sum.shape)))
+        if x0 is not None:
+            x0 = _req(x0, "x0", 4)
+        out = torch.empty((B, H, W, T), dtype=torch.float32, device=self.device)
+        need = lib().deqsci_reconstruct_workspace_bytes(self._h, B, H, W, T, int(m))
+        if need == 0:
+            raise DeqsciError("reconstruct: unsupported shape or history m=%d" % m)
+        if self._rws is None or self._rws.numel() < need:
+            self._rws = None
+            self._rws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        opts = _lib.SolverOpts(int(m), float(lam), float(beta), int(max_iter), float(tol), float(sigma0),
+                               float(sigma_decay), int(sigma_start_call), int(bool(final_call)), 1e-5)
+        res = _lib.SolverResult()
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_reconstruct(self._h, y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                           x0.data_ptr() if x0 is not None else None, out.data_ptr(),
+                                           ctypes.byref(opts), self._rws.data_ptr(), self._rws.numel(),
+                                           ctypes.byref(res), B, H, W, T, _stream(y)), "deqsci_reconstruct")
+        return out, res
 
     def debug_hidden_layer(self, layer, act_in, NF, Hc, Wc):
         """Testing hook: act_in fp16 [2, NF, Hc, Wc, 64] (hi plane, lo plane) -> same shape."""

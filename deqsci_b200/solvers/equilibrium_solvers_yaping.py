@@ -29,46 +29,71 @@ class EquilibriumProxGradSCI(nn.Module):
         self.maxval = maxval
         self.eta = eta
         self.y = 0                    # mean of the measurement the sigma schedule belongs to
-        self._sigma = _SIGMA0
+        self._n = 0                   # calls made since the last reset: the next call uses sigma_table[_n]
         self._y_key = None
+        self._undo = None
         self.n_sigma_frames = 8
 
     # ---- sigma schedule (host side) ------------------------------------------------------------
+    _table = [_SIGMA0]                # sigma_k = fp32(sigma_{k-1} * fp32(0.971)), shared by all instances
+
+    @classmethod
+    def sigma_at(cls, k):
+        while len(cls._table) <= k:
+            cls._table.append(np.float32(cls._table[-1] * _DECAY))
+        return cls._table[k]
+
+    @property
+    def _sigma(self):
+        """sigma used by the most recent call (60/255 before any call)."""
+        return self.sigma_at(max(self._n - 1, 0))
+
     @property
     def noise_sigma(self):
         """Per-frame sigma vector, like the reference's attribute (:394,410,413)."""
         dev = next(self.nonlinear_op.parameters()).device
         return torch.full((self.n_sigma_frames,), float(self._sigma), dtype=torch.float32, device=dev)
 
-    def _advance_sigma(self, y):
-        """Reference :409-413: `if self.y != y.mean(): reset else: sigma *= 0.971`.  The mean of a
-        tensor we have already seen (same storage, same version) is not recomputed, so a solver
-        loop costs one device sync per new measurement instead of one per call."""
-        self._undo = (self.y, self._sigma, self._y_key)      # state before this call (rollback_call)
+    def _observe(self, y):
+        """Reference :409-412: `if self.y != y.mean(): reset`.  The mean of a tensor we have already seen
+        (same storage, same version) is not recomputed, so a solver loop costs one device sync per new
+        measurement instead of one per call.  Returns True when the schedule was reset."""
         key = (y.data_ptr(), y._version, tuple(y.shape), str(y.device))
         if key != self._y_key:
             mean = float(y.mean())
             self._y_key = key
             if self.y != mean:
                 self.y = mean
-                self._sigma = _SIGMA0
-                return self._sigma
-        self._sigma = np.float32(self._sigma * _DECAY)
-        return self._sigma
+                self._n = 0
+                return True
+        return False
+
+    def _advance_sigma(self, y):
+        """sigma of this call: 60/255 right after a reset, else the previous one times 0.971 (:413).
+        (The very first call of a measurement whose mean equals the stored one decays, as in the
+        reference.)"""
+        self._undo = (self.y, self._n, self._y_key)          # state before this call (rollback_call)
+        if self._observe(y):
+            self._n = 1
+            return self.sigma_at(0)
+        if self._n == 0:          # no reset on a never-reset schedule: the reference decays its initial 60/255
+            self._n = 1
+        self._n += 1
+        return self.sigma_at(self._n - 1)
 
     def rollback_call(self):
         """Undoes the schedule advance of the most recent forward() (a solver that queued one
         speculative iteration past convergence calls this; the map has no other per-call state in
         eval mode)."""
-        if self.nonlinear_op.tag == 'ffdnet' and getattr(self, "_undo", None) is not None:
-            self.y, self._sigma, self._y_key = self._undo
+        if self.nonlinear_op.tag == 'ffdnet' and self._undo is not None:
+            self.y, self._n, self._y_key = self._undo
             self._undo = None
 
     def skip_call(self):
         """Advances the sigma schedule as one forward() call would, without computing anything
         (DEQFixedPoint uses it for the reference's wasted second post-solver call at inference)."""
         if self.nonlinear_op.tag == 'ffdnet':
-            self._sigma = np.float32(self._sigma * _DECAY)
+            self._n = max(self._n, 1) + 1
 
     # ---- forward -----------------------------------------------------------------------------------
     def _native_ok(self, z):

@@ -209,9 +209,39 @@ class DEQFixedPoint(nn.Module):
         op = getattr(self.f, "nonlinear_op", None)
         return (not torch.is_grad_enabled()) or (op is not None and not op.training)
 
+    # ---- device-resident driver: the whole inference forward() as one C-ABI call --------------------
+    def _driver_ok(self, z):
+        import os
+        f = self.f
+        return (os.environ.get("DEQSCI_DRIVER", "1") != "0" and self.solver is andersonexp
+                and hasattr(f, "_native_ok") and f._native_ok(z)
+                and f.A is cg_utils.A_torch_ and f.At is cg_utils.At_torch_
+                and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"} and self.kwargs.get("max_iter", 50) >= 2
+                and not f._forward_pre_hooks and not f._forward_hooks)
+
+    def _forward_driver(self, x, Phi, Phi_sum, init_point):
+        f = self.f
+        start = 0
+        if f.nonlinear_op.tag == 'ffdnet':
+            f.n_sigma_frames = int(init_point.shape[0] * init_point.shape[3])
+            # reset-or-continue decision of the first call; a schedule that was never reset (measurement
+            # mean equal to the initial 0) decays its initial 60/255 before first use, as in the reference
+            start = 0 if f._observe(x) else max(f._n, 1)
+        kw = dict(m=5, lam=1e-4, max_iter=50, tol=1e-5, beta=1.0)
+        kw.update(self.kwargs)
+        plan = f.nonlinear_op.native_plan(init_point.device)
+        z, r = plan.reconstruct(x, Phi, Phi_sum, x0=init_point, sigma_start_call=start, final_call=True, **kw)
+        self.forward_res = float(r.residual)
+        if f.nonlinear_op.tag == 'ffdnet':
+            f._n = start + int(r.f_calls) + 1              # + the reference's second post-solver call
+            f._undo = None
+        return z
+
     def forward(self, x, Phi, Phi_sum, initial_point=None, train_flag=True):
         init_point = torch.zeros_like(Phi.expand(x.shape[0], *Phi.shape[1:])) if initial_point is None else initial_point
         bound = _BoundIterate(self.f, x, Phi, Phi_sum)
+        if self._inference() and self._driver_ok(init_point):
+            return self._forward_driver(x, Phi, Phi_sum, init_point)
         with torch.no_grad():
             z, self.forward_res = self.solver(bound, init_point, **self.kwargs)
         if self._inference():

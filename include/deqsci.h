@@ -156,6 +156,43 @@ int deqsci_residual(const float* a, const float* b, float* res, float* scratch, 
                     float res_eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (4) Whole reconstruction in one call: the device-resident driver.
+ *     z* = andersonexp(f, x0, m, lam, max_iter, tol, beta); out = f(z*)        with f = deqsci_iterate
+ *     = DEQFixedPoint.forward at inference (solvers/new_equilibrium_utils_yaping.py:248-268; the
+ *     reference's second post-solver call only feeds the backward hook and is not run).
+ *     Queues the library's kernels from a C++ loop; residuals come back through pinned memory one
+ *     iteration behind, so the device never waits for the host.  Synchronises `stream` before returning.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int m;               /* Anderson history (2..8); entry script: 5                                   */
+  float lam;           /* regulariser of the bordered system; entry script: 1e-2                       */
+  float beta;          /* mixing; entry script: 1.0                                                    */
+  int max_iter;        /* and_maxiters                                                                 */
+  float tol;           /* stop when ||F-X|| / (res_eps + ||F||) < tol (whole batch); entry script 1e-5 */
+  float sigma0;        /* FFDNet noise level of the first call after a reset: 60/255                   */
+  float sigma_decay;   /* 0.971 per call (fp32 multiply); both ignored by DnCNN plans                  */
+  int sigma_start_call;/* schedule position of the first f call of this solve (0 = fresh measurement)  */
+  int final_call;      /* 1: out = f(z*) (the reconstruction), 0: out = z*                             */
+  double res_eps;      /* 1e-5 in andersonexp (a python double there, so a double here)                */
+} deqsci_solver_opts;
+
+typedef struct {
+  double residual;     /* last residual tested (python float `forward_res` of the reference)          */
+  int iterations;      /* last solver iteration index k                                                */
+  int f_calls;         /* iterate-map evaluations that count towards the sigma schedule                */
+  int converged;       /* 1 if the tolerance stopped the loop                                          */
+  float sigma_next;    /* sigma the next call would use                                                */
+} deqsci_solver_result;
+
+size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T, int m);
+
+/* y, phi_sum [B,H,W]; phi, x0, out [B,H,W,T]; x0 may be NULL (= At(y, Phi), utils/cg_utils.py:228-229). */
+int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+                       const float* x0, float* out, const deqsci_solver_opts* opts,
+                       void* workspace, size_t workspace_bytes, deqsci_solver_result* result,
+                       int B, int H, int W, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch accounting and sampled device timing of the library's own kernels.
  * Kernel classes: 0 gap, 1 conv_first, 2 conv_hidden, 3 conv_last, 4 anderson_gram,
  * 5 anderson_solve, 6 anderson_mix  (DEQSCI_PROFILE_KINDS entries in every array below).

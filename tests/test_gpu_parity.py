@@ -366,6 +366,34 @@ def test_forward_iteration_golden(dev, small_vectors, d):
     np.testing.assert_allclose(res, v["picard6_res_" + d], rtol=1e-3)
 
 
+@pytest.mark.parametrize("d", ["ffdnet", "SimpleCNN"])
+def test_driver_equals_python_loop(dev, small_vectors, d, monkeypatch):
+    """deqsci_reconstruct (the whole forward() in one C-ABI call) vs the Python-driven solver loop:
+    same kernels in the same order => bit-identical reconstruction, residual and sigma-schedule state,
+    also across two consecutive measurements (schedule reset / continuation)."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    Phi, y = t(v["crop_Phi"], dev), t(v["crop_y"], dev)
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DEQSCI_DRIVER", mode)
+        solver = build_solver(d, dev)
+        deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=20, tol=1e-5)
+        z1 = deq.forward(y, Phi, Ps, initial_point=x0, train_flag=False)
+        r1 = deq.forward_res
+        z2 = deq.forward(y, Phi, Ps, initial_point=x0, train_flag=False)      # same tensor: schedule continues
+        y3 = (y * 0.5).contiguous()
+        z3 = deq.forward(y3, Phi, Ps, initial_point=At_torch_(y3, Phi), train_flag=False)   # new mean: reset
+        outs[mode] = (z1, r1, z2, z3, deq.forward_res, solver._n)
+    a, b = outs["1"], outs["0"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert a[1] == b[1] and a[4] == b[4] and a[5] == b[5]
+    if d == "ffdnet":
+        assert not torch.equal(a[0], a[2])       # the continued schedule really changes the result
+
+
 def test_per_iterate_trace_vs_oracle(dev, small_vectors):
     """Every iterate of a 12-iteration Anderson run vs the numpy oracle (SimpleCNN weights)."""
     from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
