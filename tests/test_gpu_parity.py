@@ -533,3 +533,57 @@ def test_dncnn_batchnorm_variant(dev):
     want = orc.dncnn_forward(x, sd, num_of_layers=17)
     got = big.to(dev)(t(x, dev)).cpu().numpy()
     assert rel_l2(got, want) <= 5e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# (8) the boundary really is a C-ABI: a plain-C host program against include/deqsci.h
+# ---------------------------------------------------------------------------------------------
+def test_c_abi_from_plain_c(dev, tmp_path):
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from deqsci_b200 import _lib
+    from deqsci_b200.native import NativeDenoiser
+    from deqsci_b200 import ops
+    cc = shutil.which("gcc") or shutil.which("cc")
+    cuda = "/usr/local/cuda"
+    if cc is None or not os.path.isdir(cuda):
+        pytest.skip("no C compiler / CUDA toolkit on this box")
+    exe = str(tmp_path / "smoke")
+    subprocess.check_call([cc, "-std=c99", "-O1", os.path.join(ROOT, "tests", "c_abi", "smoke.c"), "-o", exe,
+                           "-I", os.path.join(ROOT, "include"), "-I", cuda + "/include",
+                           "-L", os.path.dirname(_lib.LIB_PATH), "-ldeqsci", "-L", cuda + "/lib64", "-lcudart",
+                           "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-Wl,-rpath," + cuda + "/lib64", "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"residual=(\S+) iterations=(\d+) f_calls=(\d+) sum=(\S+) sumsq=(\S+)", out.stdout)
+    assert m, out.stdout
+    # the same problem through the Python host mirror (same LCG stream as smoke.c)
+    state = [12345]
+
+    def lcg():
+        state[0] = (state[0] * 1664525 + 1013904223) & 0xFFFFFFFF
+        return np.float32(np.float32(state[0] >> 8) / np.float32(16777216.0) - np.float32(0.5))
+    B, H, W, T = 2, 16, 144, 8
+    cin, cout = [1, 64, 64, 64], [64, 64, 64, 1]
+    layers = []
+    for l in range(4):
+        scale = np.float32(0.5 if l == 0 else 0.08)
+        w = np.array([lcg() * scale for _ in range(cout[l] * cin[l] * 9)], np.float32).reshape(cout[l], cin[l], 3, 3)
+        layers.append({"weight": w, "relu": l < 3})
+    n_cube = B * H * W * T
+    x, phi = np.empty(n_cube, np.float32), np.empty(n_cube, np.float32)
+    for i in range(n_cube):
+        x[i] = lcg() + np.float32(0.5)
+        phi[i] = 0.0 if lcg() < 0 else 1.0
+    xt, pt = t(x.reshape(B, H, W, T), dev), t(phi.reshape(B, H, W, T), dev)
+    plan = NativeDenoiser("dncnn", layers, precision="tc_split", device=dev)
+    z, r = plan.reconstruct(ops.gap_forward(xt, pt), pt, ops.phi_sum(pt), x0=None, m=5, lam=1e-2, beta=1.0,
+                            max_iter=12, tol=1e-5)
+    zz = z.double()
+    assert int(m.group(2)) == r.iterations and int(m.group(3)) == r.f_calls
+    # smoke.c prints 10 significant digits
+    assert abs(float(m.group(1)) - r.residual) <= 1e-8 * abs(r.residual)
+    assert abs(float(m.group(4)) - float(zz.sum())) <= 1e-8 * abs(float(zz.sum()))
+    assert abs(float(m.group(5)) - float((zz * zz).sum())) <= 1e-8 * float((zz * zz).sum())
