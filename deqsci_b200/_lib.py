@@ -27,6 +27,10 @@ class SolverResult(Structure):
                 ("sigma_next", c_float)]
 
 
+class BNParams(Structure):
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p)]
+
+
 class ConvLayer(Structure):
     _fields_ = [("cin", c_int), ("cout", c_int), ("relu", c_int),
                 ("weight_host", POINTER(c_float)), ("scale_host", POINTER(c_float)),
@@ -48,6 +52,8 @@ SIGNATURES = {
     "deqsci_denoiser_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
     "deqsci_denoise_residual": (c_int, [_P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
     "deqsci_iterate": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_iterate_train": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(BNParams), c_float, c_float,
+                                     c_int, c_int, c_int, c_int, _P]),
     "deqsci_anderson_scratch_floats": (c_size_t, [c_int, c_int, c_longlong]),
     "deqsci_anderson_update": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, c_int,
                                        c_float, c_float, _P]),

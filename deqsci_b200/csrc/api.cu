@@ -53,7 +53,10 @@ void tc2_pack_weights(const float* w, uint8_t* img);
 bool tc2_supported(int Hc, int Wc);
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                            cudaStream_t st);
+                            cudaStream_t st, double* stats = nullptr);
+int bn_train_launch(__half* act, long long plane_elems, double* stats, float* scale_shift, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    long long count, int relu, cudaStream_t st);
 size_t tc_weight_image_bytes(bool split, int cout);
 void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img);
 
@@ -199,19 +202,20 @@ int geometry(const deqsci_denoiser* h, int B, int H, int W, int T, Geometry* g) 
 extern "C" size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T) {
   Geometry g;
   if (geometry(h, B, H, W, T, &g) != DEQSCI_OK) return 0;
-  return 1024 + g.zprime_bytes + 2 * g.act_bytes;
+  return 1024 + g.zprime_bytes + 2 * g.act_bytes + 4096 /* train-mode BatchNorm statistics */;
 }
 
 static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, const float* y, const float* phi,
                      const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes, int B,
-                     int H, int W, int T, void* stream) {
+                     int H, int W, int T, void* stream, const deqsci_bn_params* bn = nullptr, float momentum = 0.f,
+                     float eps = 0.f) {
   Geometry g;
   int rc = geometry(h, B, H, W, T, &g);
   if (rc) return rc;
   DEQSCI_CHECK_ARG(z != nullptr && out != nullptr && workspace != nullptr, "null pointer");
   if (fuse_gap) DEQSCI_CHECK_ARG(y && phi && phi_sum, "iterate: null y / phi / phi_sum");
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-  const size_t need = (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + g.zprime_bytes + 2 * g.act_bytes;
+  const size_t need = (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + g.zprime_bytes + 2 * g.act_bytes + 4096;
   if (workspace_bytes < need) {
     set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     return DEQSCI_ERR_WORKSPACE;
@@ -221,6 +225,14 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
                     reinterpret_cast<__half*>(ws + g.zprime_bytes + g.act_bytes)};
   cudaStream_t st = (cudaStream_t)stream;
   const int nl = (int)h->layers.size();
+  double* bn_stats = reinterpret_cast<double*>(ws + g.zprime_bytes + 2 * g.act_bytes);      // [128]
+  float* bn_scale_shift = reinterpret_cast<float*>(bn_stats + 2 * kHidden);                  // [128]
+  if (bn) {
+    DEQSCI_CHECK_ARG(h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc) && tcf_supported(g.Wc),
+                     "train-mode BatchNorm path needs precision tc_split and conv images wider than 64 with even "
+                     "height (got %dx%d)", g.Hc, g.Wc);
+    DEQSCI_CUDA(cudaMemsetAsync(bn_stats, 0, 2 * kHidden * sizeof(double), st));
+  }
   const Layer& L0 = h->layers[0];
   if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
     // tensor-core first layer: GAP + unshuffle + split into 16-channel planes (parked in the second
@@ -241,7 +253,15 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     if (h->precision == DEQSCI_PREC_FP32)
       rc = conv_mid_fp32_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
                                 g.Wc, st);
-    else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))
+    else if (bn && bn[i].gamma) {
+      // train mode: raw conv + per-channel statistics, then batch-statistics BatchNorm (+ ReLU) in place
+      rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
+                                   g.Wc, st, bn_stats);
+      if (rc == DEQSCI_OK)
+        rc = bn_train_launch(act[cur ^ 1], g.plane_elems, bn_stats, bn_scale_shift, bn[i].gamma, bn[i].beta,
+                             bn[i].running_mean, bn[i].running_var, momentum, eps, (long long)g.NF * g.Hc * g.Wc,
+                             L.relu, st);
+    } else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))
       rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, L.scale, L.bias, L.relu, g.NF,
                                    g.Hc, g.Wc, st);
     else
@@ -273,6 +293,15 @@ extern "C" int deqsci_iterate(const deqsci_denoiser* h, const float* z, const fl
                               const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
                               int B, int H, int W, int T, void* stream) {
   return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream);
+}
+
+extern "C" int deqsci_iterate_train(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                                    const float* phi_sum, float sigma, float* out, void* workspace,
+                                    size_t workspace_bytes, const deqsci_bn_params* bn_host, float momentum, float eps,
+                                    int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(bn_host != nullptr, "iterate_train: null BatchNorm table");
+  return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream, bn_host,
+                   momentum, eps);
 }
 
 // Testing hook (declared in deqsci.h): one hidden 64->64 layer on caller-provided planes.

@@ -1,0 +1,74 @@
+// Train-mode BatchNorm2d for the hidden conv layers (nn.BatchNorm2d(64), eps 1e-5, momentum 0.1,
+// networks/ffdnet/models.py:58): batch statistics over (frames, H, W) per channel.
+//   bn_finalize : from the per-channel sum / sum of squares the conv kernel accumulated (fp64):
+//                 mean, biased variance -> scale = gamma * rsqrt(var + eps), shift = beta - mean*scale;
+//                 running_mean / running_var momentum update (unbiased variance), accumulators re-zeroed
+//   bn_apply    : y = relu(x * scale[c] + shift[c]) on the raw conv output planes, in place
+//                 (fp16 hi/lo pair -> fp32 -> affine -> re-split); 256 B per pixel read + written.
+#include "common.cuh"
+
+namespace deqsci {
+
+__global__ void bn_finalize_kernel(double* __restrict__ stats, float* __restrict__ scale_shift,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, double count) {
+  const int c = threadIdx.x;
+  if (c >= kHidden) return;
+  const double mean = stats[c] / count;
+  double var = stats[kHidden + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * rsqrtf((float)var + eps);
+  scale_shift[c] = sc;
+  scale_shift[kHidden + c] = b - (float)mean * sc;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+  stats[c] = 0.0;
+  stats[kHidden + c] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act, long long plane_elems,
+                                                       const float* __restrict__ scale_shift, int relu) {
+  __shared__ float ss[2 * kHidden];
+  if (threadIdx.x < 2 * kHidden) ss[threadIdx.x] = scale_shift[threadIdx.x];
+  __syncthreads();
+  const long long n_vec = plane_elems / 8;     // 8 channels (16 bytes per plane) per step
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint4 h4 = *reinterpret_cast<const uint4*>(act + i * 8);
+    uint4 l4 = *reinterpret_cast<const uint4*>(act + plane_elems + i * 8);
+    __half* hh = reinterpret_cast<__half*>(&h4);
+    __half* ll = reinterpret_cast<__half*>(&l4);
+    const int c0 = (int)((i * 8) & (kHidden - 1));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = fmaf(join_f16(hh[e], ll[e]), ss[c0 + e], ss[kHidden + c0 + e]);
+      if (relu) v = fmaxf(v, 0.f);
+      split_f16(v, hh[e], ll[e]);
+    }
+    *reinterpret_cast<uint4*>(act + i * 8) = h4;
+    *reinterpret_cast<uint4*>(act + plane_elems + i * 8) = l4;
+  }
+}
+
+// stats: device double[128] (zero on entry, zero again on exit); scale_shift: device float[128] scratch
+int bn_train_launch(__half* act, long long plane_elems, double* stats, float* scale_shift, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    long long count, int relu, cudaStream_t st) {
+  bn_finalize_kernel<<<1, kHidden, 0, st>>>(stats, scale_shift, gamma, beta, running_mean, running_var, momentum, eps,
+                                            (double)count);
+  DEQSCI_LAUNCH_CHECK();
+  long long blocks = (plane_elems / 8 + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  ProfScope prof(PK_GAP, st);
+  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(act, plane_elems, scale_shift, relu);
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+}  // namespace deqsci

@@ -114,6 +114,7 @@ struct Params {
   int tiles_x, strips_y, strip_rows;
   long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
   long long n_pair_items;
+  double* stats;              // STATS kernels: [128] = per-channel sum, then sum of squares
   int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
   __half* dbg_out_hi;
   __half* dbg_out_lo;
@@ -134,6 +135,9 @@ __device__ __forceinline__ Strip decode(const Params& p, long long strip) {
   return s;
 }
 
+// STATS = true (train-mode BatchNorm): additionally accumulates per-output-channel sum and sum of
+// squares of the values it writes (over valid pixels) into p.stats[0..63] / [64..127] (fp64 atomics).
+template <bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
                         const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
@@ -264,8 +268,14 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     const uint32_t tempty_leader0 = mapa(bar_tempty(0), 0), tempty_leader1 = mapa(bar_tempty(1), 0);
     int buf = 0;
     uint32_t tphase = 0;
+    float st_sum[STATS ? 32 : 1], st_sq[STATS ? 32 : 1];     // this thread's 32 channels, over all its pixels
+    if (STATS) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+    }
     for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
       const Strip s = decode(p, 2 * item + rank);
+      const bool px_valid = s.real && (s.w0 + quarter * 32 + lane) < p.Wc;
       for (int j = 0; j < p.strip_rows; ++j) {
         const int h = s.h0 + j;
         mbar_wait(bar_tfull(buf), tphase);
@@ -289,6 +299,10 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
                              __uint_as_float(acc[i + u]));
               a = fmaf(a, aff_s[c], aff_s[64 + c]);
               v[u] = p.relu ? fmaxf(a, 0.f) : a;
+              if (STATS && px_valid) {
+                st_sum[part * 16 + i + u] += v[u];
+                st_sq[part * 16 + i + u] = fmaf(v[u], v[u], st_sq[part * 16 + i + u]);
+              }
             }
             __half h0, l0, h1, l1;
             split_f16(v[0], h0, l0);
@@ -342,6 +356,21 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
       }
     }
     if (lane == 0) bulk_wait0();
+    if (STATS) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float a = st_sum[c], b = st_sq[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+          atomicAdd(p.stats + half * 32 + c, (double)a);
+          atomicAdd(p.stats + 64 + half * 32 + c, (double)b);
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -414,7 +443,7 @@ bool tc2_supported(int Hc, int Wc) {
 
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                            cudaStream_t st) {
+                            cudaStream_t st, double* stats) {
   tc2::Params p;
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
@@ -432,6 +461,7 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.n_pair_items = (p.n_strips + 1) / 2;
   static const int skip_store = getenv("DEQSCI_TC_DEBUG_SKIP_STORE") ? atoi(getenv("DEQSCI_TC_DEBUG_SKIP_STORE")) : 0;
   p.debug_skip_store = skip_store;
+  p.stats = stats;
   p.dbg_out_hi = act_out;
   p.dbg_out_lo = act_out + plane_elems;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
@@ -441,11 +471,18 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   if ((rc = make_plane_map(&out_hi, act_out, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
-  DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   tc2::kSmemBytes));
   ProfScope prof(PK_CONV_HIDDEN, st);
-  tc2::conv_hidden_2cta_kernel<<<(unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st>>>(in_hi, in_lo, out_hi,
-                                                                                               out_lo, p);
+  if (stats) {
+    DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tc2::kSmemBytes));
+    tc2::conv_hidden_2cta_kernel<true><<<(unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st>>>(
+        in_hi, in_lo, out_hi, out_lo, p);
+  } else {
+    DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tc2::kSmemBytes));
+    tc2::conv_hidden_2cta_kernel<false><<<(unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st>>>(
+        in_hi, in_lo, out_hi, out_lo, p);
+  }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }

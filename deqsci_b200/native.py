@@ -119,6 +119,42 @@ class NativeDenoiser:
                                        _stream(z)), "deqsci_iterate")
         return out
 
+    def iterate_train(self, z, y, phi, phi_sum, sigma, bn_modules, out=None):
+        """One call of the iterate map with the denoiser in TRAIN mode (deqsci_iterate_train):
+        batch-statistics BatchNorm, running statistics of `bn_modules` updated in place once (momentum,
+        unbiased variance, num_batches_tracked += 1), like nn.BatchNorm2d.  bn_modules[i] is the
+        BatchNorm2d that follows conv layer i of the plan, or None.  The plan must be a train plan
+        (BatchNorm not folded)."""
+        z, y = _req(z, "z", 4), _req(y, "y", 3)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
+        self._check_dev(z)
+        B, H, W, T = (int(s) for s in z.shape)
+        if len(bn_modules) != self.num_layers:
+            raise DeqsciError("iterate_train: %d BatchNorm slots for %d conv layers" % (len(bn_modules), self.num_layers))
+        arr = (_lib.BNParams * self.num_layers)()
+        momentum, eps = 0.1, 1e-5
+        for i, bn in enumerate(bn_modules):
+            if bn is None:
+                continue
+            if bn.momentum is None or not bn.track_running_stats:
+                raise DeqsciError("native train-mode BatchNorm needs momentum and running statistics")
+            momentum, eps = float(bn.momentum), float(bn.eps)
+            arr[i].gamma = bn.weight.data_ptr() if bn.affine else None
+            arr[i].beta = bn.bias.data_ptr() if bn.affine else None
+            arr[i].running_mean = bn.running_mean.data_ptr()
+            arr[i].running_var = bn.running_var.data_ptr()
+        if out is None:
+            out = torch.empty_like(z)
+        ws = self._workspace(B, H, W, T)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_iterate_train(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                             float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), arr, momentum,
+                                             eps, B, H, W, T, _stream(z)), "deqsci_iterate_train")
+        for bn in bn_modules:
+            if bn is not None and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        return out
+
     def reconstruct(self, y, phi, phi_sum, x0=None, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5,
                     sigma_start_call=0, final_call=True, sigma0=60 / 255, sigma_decay=0.971):
         """Whole DE-GAP reconstruction in ONE C-ABI call (deqsci_reconstruct): andersonexp on the
@@ -163,22 +199,26 @@ class NativePlanCache:
     """Mixin for the nn.Module mirrors: builds / caches a NativeDenoiser per (device, precision)
     and rebuilds it when any parameter or buffer changed (tensor version counters)."""
 
-    def _plan_layers(self):  # -> (kind, [layer dicts])
+    def _plan_layers(self, train=False):  # -> (kind, [layer dicts]); train=True: BatchNorm NOT folded
         raise NotImplementedError
 
-    def _plan_signature(self):
-        return tuple((id(t), t._version, t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+    def _plan_signature(self, train=False):
+        # the train plan holds conv weights only: running statistics change on every call and must not
+        # invalidate it
+        tensors = [p for p in self.parameters() if p.dim() == 4] if train else \
+            list(self.parameters()) + list(self.buffers())
+        return tuple((id(t), t._version, t.data_ptr()) for t in tensors)
 
-    def native_plan(self, device, precision=None):
+    def native_plan(self, device, precision=None, train=False):
         precision = precision or getattr(self, "precision", None) or default_precision()
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         cache = self.__dict__.setdefault("_native_cache", {})
-        key = (str(device), precision)
-        sig = self._plan_signature()
+        key = (str(device), precision, bool(train))
+        sig = self._plan_signature(train)
         hit = cache.get(key)
         if hit is None or hit[0] != sig:
-            kind, layers = self._plan_layers()
+            kind, layers = self._plan_layers(train) if train else self._plan_layers()
             cache[key] = (sig, NativeDenoiser(kind, layers, precision, device))
         return cache[key][1]

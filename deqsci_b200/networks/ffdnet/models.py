@@ -50,9 +50,21 @@ class IntermediateDnCNN(nn.Module):
         return self.itermediate_dncnn(x)
 
 
-def sequential_to_plan_layers(seq):
+def sequential_bn_slots(seq):
+    """[BatchNorm2d or None] per conv layer of the Sequential (the BatchNorm that follows it)."""
+    slots = []
+    for mod in seq:
+        if isinstance(mod, nn.Conv2d) or hasattr(mod, "plan_weight"):
+            slots.append(None)
+        elif isinstance(mod, nn.BatchNorm2d):
+            slots[-1] = mod
+    return slots
+
+
+def sequential_to_plan_layers(seq, fold_bn=True):
     """nn.Sequential of Conv2d / BatchNorm2d / ReLU -> layer dicts for NativeDenoiser, with
-    eval-mode BatchNorm folded to out = conv*scale + bias (computed in fp64, stored fp32)."""
+    eval-mode BatchNorm folded to out = conv*scale + bias (computed in fp64, stored fp32).
+    fold_bn=False (train plan): BatchNorm layers are left to deqsci_iterate_train."""
     layers = []
     for mod in seq:
         if isinstance(mod, nn.Conv2d) or hasattr(mod, "plan_weight"):
@@ -61,6 +73,8 @@ def sequential_to_plan_layers(seq):
                 raise DeqsciError("native conv stack supports 3x3 bias-free convolutions only")
             layers.append({"weight": w.detach().float().cpu(), "scale": None, "bias": None, "relu": False})
         elif isinstance(mod, nn.BatchNorm2d):
+            if not fold_bn:
+                continue
             var = mod.running_var.detach().double().cpu()
             mean = mod.running_mean.detach().double().cpu()
             gamma = mod.weight.detach().double().cpu() if mod.affine else torch.ones_like(var)
@@ -97,10 +111,22 @@ class FFDNet(nn.Module, NativePlanCache):
         self.upsamplefeatures = UpSampleFeatures()
 
     # -- native plan -----------------------------------------------------------------------
-    def _plan_layers(self):
+    def _plan_layers(self, train=False):
         if self.num_input_channels != 1:
             raise DeqsciError("the native FFDNet path covers the grayscale network (the SCI path); RGB is not on it")
-        return "ffdnet", sequential_to_plan_layers(self.intermediate_dncnn.itermediate_dncnn)
+        return "ffdnet", sequential_to_plan_layers(self.intermediate_dncnn.itermediate_dncnn, fold_bn=not train)
+
+    def bn_slots(self):
+        return sequential_bn_slots(self.intermediate_dncnn.itermediate_dncnn)
+
+    def native_train_ok(self, z):
+        """Train-mode forward solve (no_grad) on the native kernels: cube [B,H,W,T] whose half-resolution
+        frames are wider than 64 pixels with even height (the CTA-pair conv kernel's tiles)."""
+        from ...native import default_precision
+        H, W = int(z.shape[1]), int(z.shape[2])
+        return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.num_input_channels == 1
+                and (getattr(self, "precision", None) or default_precision()) == "tc_split"
+                and H % 2 == 0 and W % 2 == 0 and W // 2 > 64 and (H // 2) % 2 == 0)
 
     def uses_native(self, x):
         # train mode means batch-statistics BatchNorm (and running-stat updates) on every call, which

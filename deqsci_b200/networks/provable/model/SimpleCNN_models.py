@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ...._lib import DeqsciError
 from ....native import NativePlanCache
-from ...ffdnet.models import sequential_to_plan_layers
+from ...ffdnet.models import sequential_bn_slots, sequential_to_plan_layers
 from .conv_sn_chen import conv_spectral_norm
 
 
@@ -38,10 +38,24 @@ class DnCNN(nn.Module, NativePlanCache):
         mods.append(conv_layer(features, channels, sigmas[-1]))
         self.dncnn = nn.Sequential(*mods)
 
-    def _plan_layers(self):
+    def _plan_layers(self, train=False):
         if self.channels != 1:
             raise DeqsciError("the native DnCNN path covers single-channel frames (the SCI path)")
-        return "dncnn", sequential_to_plan_layers(self.dncnn)
+        return "dncnn", sequential_to_plan_layers(self.dncnn, fold_bn=not train)
+
+    def bn_slots(self):
+        return sequential_bn_slots(self.dncnn)
+
+    def native_train_ok(self, z):
+        """Train-mode forward solve (no_grad) with BatchNorm on the native kernels (plain conv / BatchNorm /
+        ReLU stacks only: the spectral-norm power iteration is per-call state the plan does not express)."""
+        from ....native import default_precision
+        H, W = int(z.shape[1]), int(z.shape[2])
+        plain = all(isinstance(m, (nn.Conv2d, nn.ReLU, nn.BatchNorm2d)) for m in self.dncnn)
+        return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.channels == 1 and plain
+                and any(isinstance(m, nn.BatchNorm2d) for m in self.dncnn)
+                and (getattr(self, "precision", None) or default_precision()) == "tc_split"
+                and W > 64 and H % 2 == 0)
 
     def _stateless_in_train_mode(self):
         return all(isinstance(m, (nn.Conv2d, nn.ReLU)) for m in self.dncnn)

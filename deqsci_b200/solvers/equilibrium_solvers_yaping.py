@@ -116,6 +116,17 @@ class EquilibriumProxGradSCI(nn.Module):
             fb = self.A(z, Phi)
             z = z + self.At((y - fb) / Phi_sum, Phi)
             return plan.denoise_residual(z, sigma, out=out)
+        op = self.nonlinear_op
+        if (tag in ('ffdnet', 'denoiser') and getattr(op, "native_train_ok", lambda t: False)(z)
+                and self.A is cg_utils.A_torch_ and self.At is cg_utils.At_torch_):
+            # train mode under no_grad (the DEQ forward solve while training): batch-statistics BatchNorm
+            # on the native kernels, running statistics updated once per call like nn.BatchNorm2d
+            sigma = 0.0
+            if tag == 'ffdnet':
+                self.n_sigma_frames = bsz * c
+                sigma = float(self._advance_sigma(y))
+            plan = op.native_plan(z.device, train=True)
+            return plan.iterate_train(z, y, Phi, Phi_sum, sigma, op.bn_slots(), out=out)
         if not z.is_cuda and not (self.nonlinear_op.training and torch.is_grad_enabled()):
             raise DeqsciError("EquilibriumProxGradSCI inference on %s: deqsci_b200 has no CPU path" % z.device)
         return self._autograd_forward(z, y, Phi, Phi_sum)

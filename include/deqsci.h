@@ -123,6 +123,28 @@ int deqsci_iterate(const deqsci_denoiser* h, const float* z, const float* y, con
                    void* workspace, size_t workspace_bytes,
                    int B, int H, int W, int T, void* stream);
 
+/* The iterate map with the denoiser in TRAIN mode (nn.Module.train(): batch-statistics BatchNorm,
+ * as the reference runs its forward solve while training).  The plan must have been
+ * created WITHOUT folded BatchNorm (scale_host = bias_host = NULL on the BatchNorm layers).
+ * bn_host[i] describes the BatchNorm2d that follows conv layer i (all NULL = none): device pointers to
+ * gamma, beta (may be NULL = 1 / 0) and to running_mean / running_var, which are UPDATED in place with
+ * `momentum` exactly once per call, like PyTorch (unbiased variance; the caller increments
+ * num_batches_tracked).  Per BatchNorm layer: conv with per-channel sum / sum-of-squares epilogue,
+ * a 64-thread finalize kernel, an in-place normalise + ReLU pass.  Needs precision TC_SPLIT and conv
+ * images wider than 64 pixels with even height. */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+} deqsci_bn_params;
+
+int deqsci_iterate_train(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                         const float* phi_sum, float sigma, float* out,
+                         void* workspace, size_t workspace_bytes,
+                         const deqsci_bn_params* bn_host, float momentum, float eps,
+                         int B, int H, int W, int T, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Anderson acceleration state update (andersonexp / anderson,
  *     solvers/new_equilibrium_utils_yaping.py:114-189).  History X, F, G : [m, B, N] fp32 — slot-major,

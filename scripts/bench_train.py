@@ -5,10 +5,10 @@ one process per GPU, gradients averaged with ONE flat NCCL all-reduce (deqsci_b2
     python scripts/bench_train.py --steps 3 --warmup 1 --batch 2
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_train.py ...
 
-Reports step time (max over ranks, CUDA events), the all-reduce time inside it, and which parts ran on
-the library's kernels: the backward Anderson solve (GAP-projector VJP kernel + Anderson kernels) is
-native; the train-mode forward solve (batch-statistics BatchNorm) and the graph-attached f call run on
-PyTorch/cuDNN pinned to fp32.  Not the driver's bench contract (that is bench.py); a side measurement."""
+Reports step time (max over ranks, CUDA events) and the all-reduce time inside it.  The train-mode forward
+solve (batch-statistics BatchNorm, deqsci_iterate_train) and the backward Anderson solve (GAP-projector VJP
+kernel + Anderson kernels) run on the library's kernels; the single graph-attached f call and its backward
+run on PyTorch/cuDNN pinned to fp32.  Not the driver's bench contract (that is bench.py); a side measurement."""
 import argparse
 import json
 import os
@@ -77,7 +77,7 @@ def main():
                           "allreduce_floats": int(n), "steps_per_s": 1e3 / float(np.mean(step_ms)),
                           "measurements_per_s": world * args.batch * 1e3 / float(np.mean(step_ms)),
                           "forward_res": deq.forward_res, "backward_res": deq.backward_res, "loss": losses,
-                          "native": "backward Anderson solve + GAP VJP; forward solve/autograd call on cuDNN fp32"}))
+                          "native": "forward solve (train-mode BatchNorm kernels), backward Anderson solve + GAP VJP; the one graph-attached f call on cuDNN fp32"}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -201,13 +201,14 @@ def stage_dncnn_bn():
     print("dncnn_bn", y.shape, float(y.abs().max()))
 
 
-def stage_train():
+def stage_train(wide=False):
     """One implicit-differentiation training step (reference training/sci_equilibrium_training.py:54-75)
-    on a 32x32x8 crop, B=2, max_iter=12, denoiser in train mode: loss and parameter gradients."""
+    on a 32x32x8 crop (wide: 32x160x8, large enough for the native train-mode kernels), B=2,
+    max_iter=12, denoiser in train mode: loss, parameter gradients, BatchNorm running statistics."""
     ref_import.install_shims()
     from utils.cg_utils import A_torch_, At_torch_
     gt, mask, meas = load_scene_ref("traffic")
-    C = (slice(100, 132), slice(110, 142))
+    C = (slice(100, 132), slice(48, 208)) if wide else (slice(100, 132), slice(110, 142))
     gt_c = torch.from_numpy(np.stack([gt[C][..., 0:8], gt[C][..., 16:24]]))
     Phi_c = torch.from_numpy(np.stack([mask[C], mask[C]]))
     y_c = A_torch_(gt_c, Phi_c)
@@ -235,13 +236,17 @@ def stage_train():
                     out["grad_%s::%s" % (d, n_)] = p_.grad.numpy().copy()
         out["gradnames_" + d] = np.array(names)
         out["gradnorms_" + d] = np.array(norms)
+        for n_, b_ in solver.named_buffers():
+            if n_.endswith("3.running_mean") or n_.endswith("3.running_var") or n_.endswith("39.running_var") \
+                    or n_.endswith("3.num_batches_tracked"):
+                out["buf_%s::%s" % (d, n_)] = b_.numpy().copy()
         print(d, "loss", float(loss), "fres", deq.forward_res, "bres", deq.backward_res, "n grads", len(names))
-    np.savez_compressed(os.path.join(HERE, "train_vectors.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "train_wide_vectors.npz" if wide else "train_vectors.npz"), **out)
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "dncnn_bn"])
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "train_wide", "dncnn_bn"])
     ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
     ap.add_argument("--scenes", nargs="*", default=SCENES)
     a = ap.parse_args()
@@ -252,6 +257,8 @@ if __name__ == "__main__":
         stage_small()
     elif a.stage == "train":
         stage_train()
+    elif a.stage == "train_wide":
+        stage_train(wide=True)
     elif a.stage == "dncnn_bn":
         stage_dncnn_bn()
     else:

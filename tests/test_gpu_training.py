@@ -36,11 +36,27 @@ def _step(d, v, dev):
     return solver, deq, rec, loss
 
 
+@pytest.fixture(scope="module")
+def train_wide_vectors():
+    return dict(np.load(os.path.join(GOLDEN, "train_wide_vectors.npz")))
+
+
 @pytest.mark.parametrize("d", ["SimpleCNN", "ffdnet"])
-def test_training_step_gradients_vs_reference(train_vectors, d):
-    v = train_vectors
+@pytest.mark.parametrize("wide", [False, True])
+def test_training_step_gradients_vs_reference(train_vectors, train_wide_vectors, d, wide):
+    """wide=True: 32x160x8 crops, where FFDNet's train-mode forward solve runs on the native kernels
+    (batch-statistics BatchNorm, running statistics updated per call); wide=False: 32x32x8 crops, where
+    it runs on PyTorch ops.  Same bar either way."""
+    v = train_wide_vectors if wide else train_vectors
     dev = torch.device("cuda", 0)
     solver, deq, rec, loss = _step(d, v, dev)
+    for k in v:                                        # BatchNorm running statistics after the step
+        if k.startswith("buf_%s::" % d):
+            got_b = dict(solver.named_buffers())[k.split("::", 1)[1]].cpu().numpy()
+            if k.endswith("num_batches_tracked"):
+                assert int(got_b) == int(v[k])
+            else:
+                assert rel_l2(got_b, v[k]) <= 1e-3, k
     assert rel_l2(rec.detach().cpu().numpy(), v["rec_" + d]) <= 1e-3
     assert abs(float(loss) - float(v["loss_" + d])) <= 1e-3 * float(v["loss_" + d])
     assert abs(deq.forward_res - float(v["fres_" + d])) <= 1e-2 * float(v["fres_" + d])
@@ -71,3 +87,47 @@ def test_gradient_allreduce_two_gpus(train_vectors):
                         os.path.join(root, "scripts", "train_step_nccl.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ALLREDUCE_OK" in r.stdout
+
+
+@pytest.mark.parametrize("kind", ["ffdnet", "dncnn_bn"])
+def test_train_mode_batchnorm_native_vs_torch(kind):
+    """One train-mode iterate-map call under no_grad (what the DEQ forward solve does while training):
+    native kernels with batch-statistics BatchNorm (deqsci_iterate_train) vs the PyTorch evaluation of
+    the same module, incl. the running statistics both leave behind after two calls."""
+    import copy
+    from test_gpu_parity import build_solver
+    from deqsci_b200.networks.provable.model.models import DnCNN
+    from deqsci_b200.solvers.equilibrium_solvers_yaping import EquilibriumProxGradSCI
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_, Phi_sum_
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    if kind == "ffdnet":
+        a = build_solver("ffdnet", dev)
+    else:
+        net = DnCNN(channels=1, num_of_layers=6)
+        a = EquilibriumProxGradSCI(A_torch_, At_torch_, net, 0.2).to(dev)
+    a.train()
+    b = copy.deepcopy(a)
+    g = torch.Generator().manual_seed(2)
+    shape = (2, 32, 160, 8) if kind == "ffdnet" else (2, 16, 136, 8)
+    z = torch.rand(shape, generator=g).to(dev)
+    Phi = (torch.rand(shape, generator=g) < 0.5).float().to(dev)
+    y = A_torch_(torch.rand(shape, generator=g).to(dev), Phi)
+    Ps = Phi_sum_(Phi)
+    with torch.no_grad():
+        assert a.nonlinear_op.native_train_ok(z)
+        n1 = a(z, y, Phi, Ps)
+        n2 = a(n1, y, Phi, Ps)
+        t1 = b._autograd_forward(z, y, Phi, Ps)
+        t2 = b._autograd_forward(t1, y, Phi, Ps)
+    assert rel_l2(n1.cpu().numpy(), t1.cpu().numpy()) <= 2e-5
+    assert rel_l2(n2.cpu().numpy(), t2.cpu().numpy()) <= 5e-5
+    bn_a = [m for m in a.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    bn_b = [m for m in b.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    assert len(bn_a) == len(bn_b) > 0
+    for ma, mb in zip(bn_a, bn_b):
+        assert int(ma.num_batches_tracked) == int(mb.num_batches_tracked) == (2 if kind == "dncnn_bn" else int(mb.num_batches_tracked))
+        assert rel_l2(ma.running_mean.cpu().numpy(), mb.running_mean.cpu().numpy()) <= 1e-4
+        assert rel_l2(ma.running_var.cpu().numpy(), mb.running_var.cpu().numpy()) <= 1e-4
+    if kind == "ffdnet":
+        assert a._n == b._n == 2
