@@ -587,3 +587,24 @@ def test_c_abi_from_plain_c(dev, tmp_path):
     assert abs(float(m.group(1)) - r.residual) <= 1e-8 * abs(r.residual)
     assert abs(float(m.group(4)) - float(zz.sum())) <= 1e-8 * abs(float(zz.sum()))
     assert abs(float(m.group(5)) - float((zz * zz).sum())) <= 1e-8 * float((zz * zz).sum())
+
+
+def test_error_paths_on_device(dev):
+    """Loud failures: FFDNet needs even H and W; a too-small workspace is refused, not overrun."""
+    import ctypes
+    import deqsci_b200
+    from deqsci_b200 import _lib
+    solver = build_solver("ffdnet", dev)
+    plan = solver.nonlinear_op.native_plan(dev)
+    z = torch.rand(1, 15, 16, 8, device=dev)
+    with pytest.raises(deqsci_b200.DeqsciError, match="even H and W"):
+        plan.denoise_residual(z, 0.1)
+    z = torch.rand(1, 16, 16, 8, device=dev)
+    out = torch.empty_like(z)
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)
+    rc = _lib.lib().deqsci_denoise_residual(plan._h, z.data_ptr(), ctypes.c_float(0.1), out.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), 1, 16, 16, 8, None)
+    assert rc == -3 and b"workspace too small" in _lib.lib().deqsci_last_error()
+    with pytest.raises(deqsci_b200.DeqsciError):
+        plan.iterate(z, torch.rand(1, 16, 16, device=dev), torch.rand(1, 16, 8, 8, device=dev),
+                     torch.rand(1, 16, 16, device=dev), 0.1)                 # inconsistent shapes

@@ -123,3 +123,29 @@ def test_aliases_expose_reference_module_paths():
     assert E2 is EquilibriumProxGradSCI and A2 is A_torch_ and F2 is FFDNet
     assert all(hasattr(eq2, n) for n in ("andersonexp", "anderson", "forward_iteration", "DEQFixedPoint"))
     assert hasattr(LinearOperator, "gramian")
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Error behaviour of the C-ABI: bad arguments return a negative status and leave a message in
+    deqsci_last_error() before any CUDA call is made (so this runs on a CPU-only host)."""
+    L = _lib.lib()
+    assert L.deqsci_gap_forward(None, None, None, 1, 4, 4, 8, None) == -1
+    assert b"null" in L.deqsci_last_error()
+    assert L.deqsci_gap_step(1, 1, 1, 1, 1, 0, 4, 4, 8, None) == -1            # B = 0
+    assert b"non-positive" in L.deqsci_last_error()
+    assert L.deqsci_anderson_update(1, 1, 1, 1, 1, 1, 1, 2, 9, 64, 0, 1, 0.01, 1e-5, None) == -1   # m = 9
+    assert b"m=9" in L.deqsci_last_error()
+    assert L.deqsci_anderson_mix(1, 1, 1, 2, 5, 64, 7, 3, 1.0, None) == -1    # slot out of range
+    assert L.deqsci_anderson_scratch_floats(0, 5, 64) == 0
+    # denoiser plan: layer table must match the network kind
+    w = np.zeros((64, 3, 3, 3), np.float32)
+    arr = (_lib.ConvLayer * 2)()
+    arr[0].cin, arr[0].cout, arr[0].weight_host = 3, 64, w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    arr[1].cin, arr[1].cout, arr[1].weight_host = 64, 1, w.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    h = ctypes.c_void_p()
+    assert L.deqsci_denoiser_create(_lib.NET_DNCNN, _lib.PREC_FP32, 2, arr, ctypes.byref(h)) == -1
+    assert b"layer 0 is 3->64, expected 1->64" in L.deqsci_last_error() and not h.value
+    assert L.deqsci_denoiser_create(7, _lib.PREC_FP32, 2, arr, ctypes.byref(h)) == -1
+    assert L.deqsci_denoiser_workspace_bytes(None, 1, 8, 8, 8) == 0
+    assert L.deqsci_reconstruct_workspace_bytes(None, 1, 8, 8, 8, 5) == 0
+    assert L.deqsci_denoiser_destroy(None) == 0
