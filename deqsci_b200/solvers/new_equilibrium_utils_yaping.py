@@ -251,13 +251,19 @@ class DEQFixedPoint(nn.Module):
                 self.f.skip_call()
             return z
         z = self.f(z, x, Phi, Phi_sum)
-        z0 = z.clone().detach().requires_grad_()
-        f0 = self.f(z0, x, Phi, Phi_sum)
-
         # tag 'ffdnet': the denoiser sees x.data, so the Jacobian of f w.r.t. z is the GAP projector and
         # the VJP is one fused kernel (deqsci_gap_vjp) instead of a trip through the autograd graph
         native_vjp = (getattr(getattr(self.f, "nonlinear_op", None), "tag", None) == 'ffdnet' and z.is_cuda
                       and getattr(self.f, "A", None) is cg_utils.A_torch_ and getattr(self.f, "At", None) is cg_utils.At_torch_)
+        z0 = z.clone().detach().requires_grad_()
+        if native_vjp:
+            # the reference's second call f(z0) only feeds autograd.grad; its side effects (sigma step,
+            # BatchNorm running statistics) are kept, its graph is not needed
+            with torch.no_grad():
+                self.f(z0.detach(), x, Phi, Phi_sum)
+            f0 = None
+        else:
+            f0 = self.f(z0, x, Phi, Phi_sum)
 
         def backward_hook(grad):
             if native_vjp:
