@@ -608,3 +608,35 @@ def test_error_paths_on_device(dev):
     with pytest.raises(deqsci_b200.DeqsciError):
         plan.iterate(z, torch.rand(1, 16, 16, device=dev), torch.rand(1, 16, 8, 8, device=dev),
                      torch.rand(1, 16, 16, device=dev), 0.1)                 # inconsistent shapes
+
+
+# ---------------------------------------------------------------------------------------------
+# (9) the entry script with the reference's flags, on .mat files and a .ckpt in the reference's formats
+# ---------------------------------------------------------------------------------------------
+def test_entry_script_flags_mat_files_and_ckpt(dev, full_recon, tmp_path):
+    """python -m deqsci_b200.video_sci_proxgrad --denoiser SimpleCNN --inference True ... (test_cnn.sh):
+    scenes written as MATLAB v5 files with the reference's variable names, weights as a checkpoint dict
+    with the reference's keys (incl. a 'module.' prefix the entry strips).  Reported average PSNR =
+    the reference's (38.14 / 32.35 / 23.55 -> 31.35 dB)."""
+    import scipy.io as sio
+    from deqsci_b200 import video_sci_proxgrad as entry
+    data_dir = tmp_path / "test_gray"
+    data_dir.mkdir()
+    want = []
+    for scene, n in (("drop8", 1), ("runner8", 1), ("traffic", 6)):
+        gt, mask, meas = load_scene(scene)
+        m = np.round(meas * 255.0)
+        if scene != "traffic":
+            m = np.concatenate([m] + [m[:, :, :1]] * 4, axis=2)
+        sio.savemat(str(data_dir / (scene + "_cacti.mat")),
+                    {"orig": np.round(gt * 255).astype(np.uint8), "mask": mask.astype(np.uint8), "meas": m})
+        want.append(np.mean([float(full_recon["SimpleCNN_%s_%d_psnr" % (scene, i)]) for i in range(n)]))
+    sd = {"module." + k: torch.from_numpy(v) for k, v in load_weights("SimpleCNN").items()}
+    ckpt = tmp_path / "cnn.ckpt"
+    torch.save({"solver_state_dict": sd, "epoch": 7, "optimizer_state_dict": {}, "scheduler_state_dict": {}}, str(ckpt))
+    psnr = entry.main(["--savepath", str(tmp_path / "save") + "/", "--testpath", str(data_dir) + "/",
+                       "--loadpath", str(ckpt), "--denoiser", "SimpleCNN", "--inference", "True"])
+    assert abs(psnr - float(np.mean(want))) <= 0.05
+    assert abs(psnr - 31.35) <= 0.05
+    pngs = os.listdir(str(tmp_path / "save" / "img" / "test"))
+    assert len(pngs) == 64 and "drop8_cacti.mat_reconstruction_0.png" in pngs

@@ -92,3 +92,17 @@ def test_dncnn_batchnorm_variant():
     sd = {k[len("sd::"):]: v[k] for k in v if k.startswith("sd::")}
     got = orc.dncnn_forward(v["x"], sd, num_of_layers=5)
     assert rel_l2(got, v["y"]) <= 2e-6
+
+
+def test_noise_floor_fixture():
+    """tests/golden/noise_floor.npz (make_noise_floor.py): on the traffic scene with the FFDNet stand-in
+    weights two fp32 implementations of the SAME algorithm -- this numpy oracle and the reference's own
+    PyTorch run -- end up to 0.29 dB apart, with iterate norms diverging past 1e-3: the 0.05 dB / 1e-3
+    bars cannot be met there by any re-implementation (the one documented exception)."""
+    import os
+    from conftest import GOLDEN
+    v = dict(np.load(os.path.join(GOLDEN, "noise_floor.npz")))
+    diffs = [abs(float(v["traffic_%d_oracle_psnr" % i]) - float(v["traffic_%d_reference_psnr" % i])) for i in (1, 2, 5)]
+    assert max(diffs) > 0.25 and min(diffs) < 0.05
+    assert all(float(v["traffic_%d_norm_rel_dev" % i].max()) > 1e-3 for i in (1, 2, 5))
+    assert all(float(v["traffic_%d_norm_rel_dev" % i][:30].max()) < 1e-4 for i in (1, 2, 5))   # early iterates agree
