@@ -5,8 +5,11 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/deqsci.h"
+
+struct CUtensorMap_st;   // <cuda.h>'s CUtensorMap (driver API type; only tma_host.cu and the TMA kernels include it)
 
 namespace deqsci {
 
@@ -53,6 +56,12 @@ struct ProfScope {
   cudaStream_t st_;
   long long idx_;
 };
+
+// tma_host.cu
+int make_plane_map(::CUtensorMap_st* map, const __half* plane, int channels, int NF, int Hc, int Wc, int box_c,
+                   int box_w, int box_h, int swizzle_bytes);
+int pick_strip_rows(int NF, int tiles_x, int Hc, bool must_divide, long long min_items, int floor_rows);
+int env_int(const char* name, int dflt);
 
 // Activation storage between conv layers: channels-last [frames, H, W, 64], each value stored as
 // an fp16 pair  v ~= hi + lo * 2^-11  in two planes (hi plane then lo plane).  Keeps ~22 mantissa

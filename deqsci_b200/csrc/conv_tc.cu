@@ -367,42 +367,11 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 }
 
 // ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  return fn;
-}
-
 void tc_tile_shape(int Wc, int* TWm, int* THm) {
   int tw = 128;
   while (tw > 8 && tw / 2 >= Wc) tw /= 2;     // smallest power of two >= Wc, clamped to [8,128]
   *TWm = tw;
   *THm = kTileM / tw;
-}
-
-static int make_act_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int box_w, int THm) {
-  const int TWm = box_w;
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
-  cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
-  cuuint64_t strides[3] = {128, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
-  cuuint32_t box[4] = {64, (cuuint32_t)TWm, (cuuint32_t)THm, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
-  return DEQSCI_OK;
 }
 
 size_t tc_weight_image_bytes(bool split, int cout) {
@@ -446,11 +415,6 @@ static int launch_tc(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const
   return DEQSCI_OK;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 // Load mode by what fits: a split-precision hidden layer keeps 144 KB of weights resident, which
 // leaves 2 row slots (LD_ROW3); single-pass hidden layers and the N = 16 last layers have room for a
 // ring of 6 (LD_ROLL).  DEQSCI_TC_LOAD = 0 | 1 | 2 caps the mode (testing).
@@ -469,9 +433,9 @@ int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, 
   tc_tile_shape(Wc, &TWm, &THm);
   const int lm = pick_load_mode(mode, split, TWm);
   CUtensorMap map_hi, map_lo;
-  int rc = make_act_map(&map_hi, act_in, NF, Hc, Wc, lm != LD_TAP ? kTileM + 2 : TWm, THm);
+  int rc = make_plane_map(&map_hi, act_in, 64, NF, Hc, Wc, 64, lm != LD_TAP ? kTileM + 2 : TWm, THm, 128);
   if (rc) return rc;
-  rc = make_act_map(&map_lo, act_in + plane_elems, NF, Hc, Wc, lm != LD_TAP ? kTileM + 2 : TWm, THm);
+  rc = make_plane_map(&map_lo, act_in + plane_elems, 64, NF, Hc, Wc, 64, lm != LD_TAP ? kTileM + 2 : TWm, THm, 128);
   if (rc) return rc;
   TcParams p;
   p.wimg = wimg; p.scale = scale; p.bias = bias;
@@ -480,9 +444,7 @@ int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, 
   p.tiles_x = (Wc + TWm - 1) / TWm;
   p.strip_rows = 1;
   if (lm == LD_ROLL) {
-    // strips of up to 16 rows, shortened until there are >= 6 work items per SM (load balance)
-    int R = 16;
-    while (R > 2 && (long long)NF * p.tiles_x * ((Hc + R - 1) / R) < 6LL * num_sms()) R /= 2;
+    const int R = pick_strip_rows(NF, p.tiles_x, Hc, false, 6LL * num_sms(), 2);
     p.strip_rows = R;
     p.tiles_y = (Hc + R - 1) / R;
   } else {

@@ -381,37 +381,6 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 }  // namespace tc2
 
 // ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled2 get_encode2() {
-  static PFN_encodeTiled2 fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled2>(ptr);
-  }
-  return fn;
-}
-
-static int make_plane_map(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc, int box_c, int box_w,
-                          CUtensorMapSwizzle sw) {
-  PFN_encodeTiled2 enc = get_encode2();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
-  cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
-  cuuint64_t strides[3] = {128, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
-  return DEQSCI_OK;
-}
-
 size_t tc2_weight_image_bytes() { return 2 * (size_t)tc2::kWBytes; }
 
 // w [64 cout][64 cin][3][3] fp32 -> [rank][tap][64 rows][128 B], rows of rank r: [0,32) = hi(W[32r + n]),
@@ -437,7 +406,7 @@ void tc2_pack_weights(const float* w, uint8_t* img) {
 
 // true when the pair kernel can run this shape: full 128-pixel row tiles and a strip height that divides Hc
 bool tc2_supported(int Hc, int Wc) {
-  static const int enabled = getenv("DEQSCI_TC_PAIR") ? atoi(getenv("DEQSCI_TC_PAIR")) : 1;
+  static const int enabled = env_int("DEQSCI_TC_PAIR", 1);
   return enabled && Wc > 64 && Hc % 2 == 0;
 }
 
@@ -452,24 +421,23 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   // strip height: the largest power of two <= 16 dividing Hc that still leaves >= `rounds` strips per SM.
   // Longer strips amortise the pipeline refill at strip boundaries (the 4-slot ring cannot prefetch the
   // next strip's three start rows while the last tile still holds three slots)
-  int R = 16;
-  static const int rounds = getenv("DEQSCI_TC_ROUNDS") ? atoi(getenv("DEQSCI_TC_ROUNDS")) : 6;
-  while (R > 1 && (Hc % R != 0 || (long long)NF * p.tiles_x * (Hc / R) < 2LL * rounds * pairs_hw)) R /= 2;
+  static const int rounds = env_int("DEQSCI_TC_ROUNDS", 6);
+  const int R = pick_strip_rows(NF, p.tiles_x, Hc, true, 2LL * rounds * pairs_hw, 1);
   p.strip_rows = R;
   p.strips_y = Hc / R;
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;
   p.n_pair_items = (p.n_strips + 1) / 2;
-  static const int skip_store = getenv("DEQSCI_TC_DEBUG_SKIP_STORE") ? atoi(getenv("DEQSCI_TC_DEBUG_SKIP_STORE")) : 0;
+  static const int skip_store = env_int("DEQSCI_TC_DEBUG_SKIP_STORE", 0);
   p.debug_skip_store = skip_store;
   p.stats = stats;
   p.dbg_out_hi = act_out;
   p.dbg_out_lo = act_out + plane_elems;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
   int rc;
-  if ((rc = make_plane_map(&in_hi, act_in, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_plane_map(&in_lo, act_in + plane_elems, NF, Hc, Wc, 64, tc2::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_plane_map(&out_hi, act_out, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_plane_map(&in_hi, act_in, 64, NF, Hc, Wc, 64, tc2::kTileM + 2, 1, 128))) return rc;
+  if ((rc = make_plane_map(&in_lo, act_in + plane_elems, 64, NF, Hc, Wc, 64, tc2::kTileM + 2, 1, 128))) return rc;
+  if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
+  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
   ProfScope prof(PK_CONV_HIDDEN, st);
   if (stats) {

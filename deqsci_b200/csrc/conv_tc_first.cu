@@ -237,33 +237,6 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
 
 }  // namespace tcf
 
-typedef CUresult (*PFN_encodeTiledF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_map(CUtensorMap* map, const __half* plane, int channels, int NF, int Hc, int Wc, int box_c, int box_w,
-                    CUtensorMapSwizzle sw) {
-  static PFN_encodeTiledF enc = nullptr;
-  if (!enc) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      enc = reinterpret_cast<PFN_encodeTiledF>(ptr);
-  }
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
-  const cuuint64_t rb = (cuuint64_t)channels * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
-  cuuint64_t strides[3] = {rb, (cuuint64_t)Wc * rb, (cuuint64_t)Hc * Wc * rb};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
-  return DEQSCI_OK;
-}
-
 size_t tcf_weight_image_bytes() { return tcf::kWBytes; }
 
 // w [64 cout][cin][3][3] fp32 (cin = 5 or 1) -> [tap][128 rows: hi(W) | lo'(W)][16 k] fp16, 32-byte swizzle
@@ -288,7 +261,7 @@ void tcf_pack_weights(const float* w, int cin, uint8_t* img) {
 }
 
 bool tcf_supported(int Wc) {
-  static const int enabled = getenv("DEQSCI_TC_FIRST") ? atoi(getenv("DEQSCI_TC_FIRST")) : 1;
+  static const int enabled = env_int("DEQSCI_TC_FIRST", 1);
   return enabled && Wc > 64;
 }
 
@@ -300,17 +273,16 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcf::kTileM - 1) / tcf::kTileM;
-  int R = 16;
-  while (R > 2 && (long long)NF * p.tiles_x * ((Hc + R - 1) / R) < 6LL * num_sms()) R /= 2;
+  const int R = pick_strip_rows(NF, p.tiles_x, Hc, false, 6LL * num_sms(), 2);
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
   int rc;
-  if ((rc = make_map(&in_hi, planes_in, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&in_lo, planes_in + in_plane_elems, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_plane_map(&in_hi, planes_in, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
+  if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
+  if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
+  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   const int grid = (int)(p.n_items < num_sms() ? p.n_items : num_sms());
   DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    tcf::kSmemBytes));

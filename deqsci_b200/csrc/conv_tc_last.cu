@@ -235,31 +235,6 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
 
 }  // namespace tcl
 
-typedef CUresult (*PFN_encodeTiledL)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_map_l(CUtensorMap* map, const __half* plane, int NF, int Hc, int Wc) {
-  static PFN_encodeTiledL enc = nullptr;
-  if (!enc) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      enc = reinterpret_cast<PFN_encodeTiledL>(ptr);
-  }
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DEQSCI_ERR_CUDA; }
-  cuuint64_t dims[4] = {64, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)NF};
-  cuuint64_t strides[3] = {128, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
-  cuuint32_t box[4] = {64, (cuuint32_t)(tcl::kTileM + 2), 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)plane, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return DEQSCI_ERR_CUDA; }
-  return DEQSCI_OK;
-}
-
 size_t tcl_weight_image_bytes() { return tcl::kWBytes; }
 
 // w [cout][64][3][3] fp32 (cout = 4 or 1) -> [kx][32 rows][64 k] fp16, 128-byte swizzle;
@@ -284,7 +259,7 @@ void tcl_pack_weights(const float* w, int cout, uint8_t* img) {
 }
 
 bool tcl_supported(int Wc) {
-  static const int enabled = getenv("DEQSCI_TC_LAST") ? atoi(getenv("DEQSCI_TC_LAST")) : 1;
+  static const int enabled = env_int("DEQSCI_TC_LAST", 1);
   return enabled && Wc > 64;
 }
 
@@ -295,16 +270,15 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcl::kTileM - 1) / tcl::kTileM;
-  int R = 16;
-  while (R > 2 && (long long)NF * p.tiles_x * ((Hc + R - 1) / R) < 6LL * num_sms()) R /= 2;
+  const int R = pick_strip_rows(NF, p.tiles_x, Hc, false, 6LL * num_sms(), 2);
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
   p.zprime = zprime; p.out_cube = out_cube; p.H = H; p.W = W; p.T = T;
   CUtensorMap in_hi, in_lo;
   int rc;
-  if ((rc = make_map_l(&in_hi, act_in, NF, Hc, Wc))) return rc;
-  if ((rc = make_map_l(&in_lo, act_in + plane_elems, NF, Hc, Wc))) return rc;
+  if ((rc = make_plane_map(&in_hi, act_in, 64, NF, Hc, Wc, 64, tcl::kTileM + 2, 1, 128))) return rc;
+  if ((rc = make_plane_map(&in_lo, act_in + plane_elems, 64, NF, Hc, Wc, 64, tcl::kTileM + 2, 1, 128))) return rc;
   const int grid = (int)(p.n_items < num_sms() ? p.n_items : num_sms());
   ProfScope prof(PK_CONV_LAST, st);
   if (cout == 4) {
