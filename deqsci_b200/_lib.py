@@ -52,6 +52,7 @@ SIGNATURES = {
     "deqsci_denoiser_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
     "deqsci_denoise_residual": (c_int, [_P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
     "deqsci_iterate": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
+    "deqsci_denoiser_update_weights": (c_int, [_P, c_int, POINTER(_P), _P]),
     "deqsci_iterate_train": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(BNParams), c_float, c_float,
                                      c_int, c_int, c_int, c_int, _P]),
     "deqsci_anderson_scratch_floats": (c_size_t, [c_int, c_int, c_longlong]),
@@ -62,6 +63,8 @@ SIGNATURES = {
     "deqsci_reconstruct_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int, c_int]),
     "deqsci_reconstruct": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
                                    c_int, c_int, c_int, c_int, _P]),
+    "deqsci_reconstruct_train": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(SolverOpts), POINTER(BNParams), c_float,
+                                         c_float, _P, c_size_t, POINTER(SolverResult), c_int, c_int, c_int, c_int, _P]),
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),

@@ -2,6 +2,8 @@
 // deqsci_denoise_residual / deqsci_iterate.  See include/deqsci.h for the contract.
 #include <string.h>
 
+#include <map>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -38,18 +40,21 @@ int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, 
                     int T, bool do_gap, cudaStream_t st);
 size_t tcf_weight_image_bytes();
 void tcf_pack_weights(const float* w, int cin, uint8_t* img);
+void tcf_pack_map(int cin, int32_t* map);
 bool tcf_supported(int Wc);
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
                          int Wc, cudaStream_t st);
 size_t tcl_weight_image_bytes();
 void tcl_pack_weights(const float* w, int cout, uint8_t* img);
+void tcl_pack_map(int cout, int32_t* map);
 bool tcl_supported(int Wc);
 int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, const uint8_t* wimg,
                         const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                         const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
 size_t tc2_weight_image_bytes();
 void tc2_pack_weights(const float* w, uint8_t* img);
+void tc2_pack_map(int32_t* map);
 bool tc2_supported(int Hc, int Wc);
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
@@ -59,6 +64,7 @@ int bn_train_launch(__half* act, long long plane_elems, double* stats, float* sc
                     long long count, int relu, cudaStream_t st);
 size_t tc_weight_image_bytes(bool split, int cout);
 void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img);
+void tc_pack_map(int cout, bool split, int32_t* map);
 
 struct Layer {
   int cin = 0, cout = 0, relu = 0;
@@ -68,6 +74,9 @@ struct Layer {
                               // ky-transposed layout (last layer)
   float* scale = nullptr;     // [cout] or null
   float* bias = nullptr;      // [cout] or null
+  // gather maps of the device-side repack (owned by the handle, shared between layers of one shape)
+  const int32_t *map_cc = nullptr, *map_tc = nullptr, *map_tc2 = nullptr;
+  int n_cc = 0, n_tc = 0, n_tc2 = 0;      // elements (fp32 for w_cc, fp16 for the images)
 };
 
 }  // namespace deqsci
@@ -75,11 +84,14 @@ struct Layer {
 struct deqsci_denoiser {
   int kind = 0, precision = 0;
   std::vector<deqsci::Layer> layers;
+  std::map<std::string, int32_t*> maps;   // device gather maps, built on the first update_weights call
 };
 
 using namespace deqsci;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int deqsci::denoiser_num_layers(const deqsci_denoiser* h) { return h ? (int)h->layers.size() : 0; }
 
 extern "C" int deqsci_version(void) { return DEQSCI_VERSION; }
 extern "C" const char* deqsci_last_error(void) { return g_err; }
@@ -93,6 +105,7 @@ extern "C" int deqsci_denoiser_destroy(deqsci_denoiser* h) {
     if (L.scale) cudaFree(L.scale);
     if (L.bias) cudaFree(L.bias);
   }
+  for (auto& kv : h->maps) cudaFree(kv.second);
   delete h;
   return DEQSCI_OK;
 }
@@ -174,6 +187,96 @@ extern "C" int deqsci_denoiser_create(int net_kind, int precision, int num_layer
     return rc;
   }
   *out = h;
+  return DEQSCI_OK;
+}
+
+// ---- device-side weight refresh ------------------------------------------------------------------
+namespace {
+__global__ void repack_kernel(const float* __restrict__ w, const int32_t* __restrict__ map, void* __restrict__ dst,
+                              int n, int as_f32) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t m = map[i];
+  if (as_f32) {
+    reinterpret_cast<float*>(dst)[i] = m < 0 ? 0.f : w[m >> 1];
+    return;
+  }
+  __half out = __float2half_rn(0.f);
+  if (m >= 0) {
+    __half hi, lo;
+    split_f16(w[m >> 1], hi, lo);
+    out = (m & 1) ? lo : hi;
+  }
+  reinterpret_cast<__half*>(dst)[i] = out;
+}
+
+template <class Fill>
+int get_map(deqsci_denoiser* h, const std::string& key, int n, Fill fill, const int32_t** out) {
+  auto it = h->maps.find(key);
+  if (it == h->maps.end()) {
+    std::vector<int32_t> host((size_t)n, -1);
+    fill(host.data());
+    int32_t* dev = nullptr;
+    DEQSCI_CUDA(cudaMalloc(&dev, (size_t)n * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(dev, host.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); set_error("update_weights: %s", cudaGetErrorString(e)); return DEQSCI_ERR_CUDA; }
+    it = h->maps.emplace(key, dev).first;
+  }
+  *out = it->second;
+  return DEQSCI_OK;
+}
+
+int build_layer_maps(deqsci_denoiser* h, int i) {
+  Layer& L = h->layers[i];
+  if (L.map_cc) return DEQSCI_OK;
+  const int cin = L.cin, cout = L.cout, n_layers = (int)h->layers.size();
+  const bool split = h->precision == DEQSCI_PREC_TC_SPLIT;
+  char key[64];
+  int rc;
+  L.n_cc = 9 * cin * cout;
+  snprintf(key, sizeof key, "cc:%d:%d", cin, cout);
+  if ((rc = get_map(h, key, L.n_cc, [&](int32_t* m) {
+        for (int o = 0; o < cout; ++o)
+          for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < 9; ++t) m[(t * cin + c) * cout + o] = 2 * ((o * cin + c) * 9 + t);
+      }, &L.map_cc))) return rc;
+  if (L.w_tc && i == 0) {
+    L.n_tc = (int)(tcf_weight_image_bytes() / 2);
+    snprintf(key, sizeof key, "tcf:%d", cin);
+    if ((rc = get_map(h, key, L.n_tc, [&](int32_t* m) { tcf_pack_map(cin, m); }, &L.map_tc))) return rc;
+  } else if (L.w_tc) {
+    L.n_tc = (int)(tc_weight_image_bytes(split, cout) / 2);
+    snprintf(key, sizeof key, "tc:%d:%d", cout, (int)split);
+    if ((rc = get_map(h, key, L.n_tc, [&](int32_t* m) { tc_pack_map(cout, split, m); }, &L.map_tc))) return rc;
+  }
+  if (L.w_tc2 && i == n_layers - 1) {
+    L.n_tc2 = (int)(tcl_weight_image_bytes() / 2);
+    snprintf(key, sizeof key, "tcl:%d", cout);
+    if ((rc = get_map(h, key, L.n_tc2, [&](int32_t* m) { tcl_pack_map(cout, m); }, &L.map_tc2))) return rc;
+  } else if (L.w_tc2) {
+    L.n_tc2 = (int)(tc2_weight_image_bytes() / 2);
+    if ((rc = get_map(h, "tc2", L.n_tc2, [&](int32_t* m) { tc2_pack_map(m); }, &L.map_tc2))) return rc;
+  }
+  return DEQSCI_OK;
+}
+}  // namespace
+
+extern "C" int deqsci_denoiser_update_weights(deqsci_denoiser* h, int num_layers, const float* const* weight_dev,
+                                              void* stream) {
+  DEQSCI_CHECK_ARG(h && weight_dev, "update_weights: null pointer");
+  DEQSCI_CHECK_ARG(num_layers == (int)h->layers.size(), "update_weights: %d layers given, the plan has %d", num_layers,
+                   (int)h->layers.size());
+  for (int i = 0; i < num_layers; ++i) DEQSCI_CHECK_ARG(weight_dev[i] != nullptr, "update_weights: layer %d is null", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < num_layers; ++i) {
+    int rc = build_layer_maps(h, i);
+    if (rc != DEQSCI_OK) return rc;
+    Layer& L = h->layers[i];
+    repack_kernel<<<(L.n_cc + 255) / 256, 256, 0, st>>>(weight_dev[i], L.map_cc, L.w_cc, L.n_cc, 1);
+    if (L.w_tc) repack_kernel<<<(L.n_tc + 255) / 256, 256, 0, st>>>(weight_dev[i], L.map_tc, L.w_tc, L.n_tc, 0);
+    if (L.w_tc2) repack_kernel<<<(L.n_tc2 + 255) / 256, 256, 0, st>>>(weight_dev[i], L.map_tc2, L.w_tc2, L.n_tc2, 0);
+    DEQSCI_LAUNCH_CHECK();
+  }
   return DEQSCI_OK;
 }
 

@@ -71,4 +71,31 @@ int bn_train_launch(__half* act, long long plane_elems, double* stats, float* sc
   return DEQSCI_OK;
 }
 
+// Running-statistics snapshot / restore for the device-resident train-mode driver: an iteration that
+// was queued speculatively (the previous one had already converged) must not leave its momentum update
+// behind.  One block per conv layer; layers without BatchNorm have null pointers.
+struct BnRunningTable {
+  float* mean[kMaxBnLayers];
+  float* var[kMaxBnLayers];
+};
+
+__global__ void bn_running_copy_kernel(BnRunningTable t, float* __restrict__ backup, int restore) {
+  const int l = blockIdx.x, c = threadIdx.x;
+  float* b = backup + (size_t)l * 2 * kHidden;
+  if (t.mean[l]) { if (restore) t.mean[l][c] = b[c]; else b[c] = t.mean[l][c]; }
+  if (t.var[l]) { if (restore) t.var[l][c] = b[kHidden + c]; else b[kHidden + c] = t.var[l][c]; }
+}
+
+int bn_running_snapshot(const deqsci_bn_params* bn, int n_layers, float* backup, int restore, cudaStream_t st) {
+  if (n_layers > kMaxBnLayers) { set_error("train-mode driver: %d layers (max %d)", n_layers, kMaxBnLayers); return DEQSCI_ERR_INVALID; }
+  BnRunningTable t;
+  for (int i = 0; i < kMaxBnLayers; ++i) {
+    t.mean[i] = i < n_layers ? bn[i].running_mean : nullptr;
+    t.var[i] = i < n_layers ? bn[i].running_var : nullptr;
+  }
+  bn_running_copy_kernel<<<n_layers, kHidden, 0, st>>>(t, backup, restore);
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
 }  // namespace deqsci

@@ -68,6 +68,11 @@ int env_int(const char* name, int dflt);
 // bits (this split reproduces the fp32 trajectory at its noise floor) in exactly
 // the operand format the tcgen05 kind::f16 MMA consumes.
 constexpr int kHidden = 64;
+constexpr int kMaxBnLayers = 32;              // conv layers a train-mode driver call can snapshot
+
+// bn_train.cu / api.cu helpers used by the driver
+int bn_running_snapshot(const deqsci_bn_params* bn, int n_layers, float* backup, int restore, cudaStream_t st);
+int denoiser_num_layers(const deqsci_denoiser* h);
 constexpr float kLoScale = 2048.0f;           // 2^11
 constexpr float kLoInvScale = 1.0f / 2048.0f;
 
@@ -78,5 +83,23 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 __device__ __forceinline__ float join_f16(__half hi, __half lo) {
   return fmaf(__half2float(lo), kLoInvScale, __half2float(hi));
 }
+
+// The weight images (shared-memory operand layouts of the tensor-core kernels) are written through an
+// emitter -- emit(byte offset in the image, index into the [cout][cin][3][3] weights, hi or lo' half) -- so one
+// layout routine serves the host packer (PackWrite) and the gather map of the device-side repack
+// (PackMap: element -> 2*index + is_lo, -1 = zero padding; deqsci_denoiser_update_weights).
+struct PackWrite {
+  const float* w;
+  uint8_t* img;
+  void operator()(size_t byte, int src, bool lo) const {
+    const float v = w[src];
+    const __half hi = __float2half_rn(v);
+    *reinterpret_cast<__half*>(img + byte) = lo ? __float2half_rn((v - __half2float(hi)) * kLoScale) : hi;
+  }
+};
+struct PackMap {
+  int32_t* map;
+  void operator()(size_t byte, int src, bool lo) const { map[byte >> 1] = src * 2 + (lo ? 1 : 0); }
+};
 
 }  // namespace deqsci

@@ -383,27 +383,28 @@ size_t tc_weight_image_bytes(bool split, int cout) {
 // bulk-copies: per tap a K-major tile [rows n][64 k=cin] fp16 with the 128-byte swizzle (16-byte chunk
 // index XOR (row & 7)); rows [0,N) = hi(W) (zero rows for n >= cout), rows [N,2N) = lo'(W) (split
 // mode), N = 64 for hidden layers, 16 for the last layer.
-void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img) {
+template <class Emit>
+static void tc_layout(int cout, bool split, Emit emit) {
   const int n_out = cout == 64 ? 64 : 16;
   const int rows = split ? 2 * n_out : n_out;
-  memset(img, 0, (size_t)9 * rows * 128);
   for (int tap = 0; tap < 9; ++tap) {
     const int ky = tap / 3, kx = tap % 3;
     for (int n = 0; n < rows; ++n) {
       const int co = n % n_out;
       if (co >= cout) continue;
       for (int k = 0; k < 64; ++k) {
-        const float v = w[((co * 64 + k) * 3 + ky) * 3 + kx];
-        const __half hi = __float2half_rn(v);
-        __half val = hi;
-        if (n >= n_out) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
         const size_t byte = (size_t)tap * rows * 128 + (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) +
                             (size_t)(k & 7) * 2;
-        *reinterpret_cast<__half*>(img + byte) = val;
+        emit(byte, ((co * 64 + k) * 3 + ky) * 3 + kx, n >= n_out);
       }
     }
   }
 }
+void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img) {
+  memset(img, 0, tc_weight_image_bytes(split, cout));
+  tc_layout(cout, split, PackWrite{w, img});
+}
+void tc_pack_map(int cout, bool split, int32_t* map) { tc_layout(cout, split, PackMap{map}); }
 
 template <bool SPLIT, int LOAD, int MODE>
 static int launch_tc(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const TcParams& p, int grid,

@@ -385,24 +385,23 @@ size_t tc2_weight_image_bytes() { return 2 * (size_t)tc2::kWBytes; }
 
 // w [64 cout][64 cin][3][3] fp32 -> [rank][tap][64 rows][128 B], rows of rank r: [0,32) = hi(W[32r + n]),
 // [32,64) = lo'(W[32r + n - 32]); K-major fp16 rows with the 128-byte swizzle.
-void tc2_pack_weights(const float* w, uint8_t* img) {
+template <class Emit>
+static void tc2_layout(Emit emit) {
   for (int rank = 0; rank < 2; ++rank)
     for (int tap = 0; tap < 9; ++tap) {
       const int ky = tap / 3, kx = tap % 3;
       for (int n = 0; n < 64; ++n) {
         const int co = 32 * rank + (n & 31);
         for (int k = 0; k < 64; ++k) {
-          const float v = w[((co * 64 + k) * 3 + ky) * 3 + kx];
-          const __half hi = __float2half_rn(v);
-          __half val = hi;
-          if (n >= 32) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
           const size_t byte = ((size_t)rank * 9 + tap) * tc2::kTapBytesB + (size_t)n * 128 +
                               (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
-          *reinterpret_cast<__half*>(img + byte) = val;
+          emit(byte, ((co * 64 + k) * 3 + ky) * 3 + kx, n >= 32);
         }
       }
     }
 }
+void tc2_pack_weights(const float* w, uint8_t* img) { tc2_layout(PackWrite{w, img}); }
+void tc2_pack_map(int32_t* map) { tc2_layout(PackMap{map}); }
 
 // true when the pair kernel can run this shape: full 128-pixel row tiles and a strip height that divides Hc
 bool tc2_supported(int Hc, int Wc) {

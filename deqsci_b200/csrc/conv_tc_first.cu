@@ -241,24 +241,25 @@ size_t tcf_weight_image_bytes() { return tcf::kWBytes; }
 
 // w [64 cout][cin][3][3] fp32 (cin = 5 or 1) -> [tap][128 rows: hi(W) | lo'(W)][16 k] fp16, 32-byte swizzle
 // (16-byte chunk index XOR bit 2 of the row index); k >= cin is zero.
-void tcf_pack_weights(const float* w, int cin, uint8_t* img) {
-  memset(img, 0, tcf::kWBytes);
+template <class Emit>
+static void tcf_layout(int cin, Emit emit) {
   for (int tap = 0; tap < 9; ++tap) {
     const int ky = tap / 3, kx = tap % 3;
     for (int n = 0; n < 128; ++n) {
       const int co = n & 63;
       for (int k = 0; k < cin; ++k) {
-        const float v = w[((co * cin + k) * 3 + ky) * 3 + kx];
-        const __half hi = __float2half_rn(v);
-        __half val = hi;
-        if (n >= 64) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
         const size_t byte = (size_t)tap * tcf::kTapBytesB + (size_t)n * 32 + (size_t)(((k >> 3) ^ ((n >> 2) & 1)) << 4) +
                             (size_t)(k & 7) * 2;
-        *reinterpret_cast<__half*>(img + byte) = val;
+        emit(byte, ((co * cin + k) * 3 + ky) * 3 + kx, n >= 64);
       }
     }
   }
 }
+void tcf_pack_weights(const float* w, int cin, uint8_t* img) {
+  memset(img, 0, tcf::kWBytes);
+  tcf_layout(cin, PackWrite{w, img});
+}
+void tcf_pack_map(int cin, int32_t* map) { tcf_layout(cin, PackMap{map}); }
 
 bool tcf_supported(int Wc) {
   static const int enabled = env_int("DEQSCI_TC_FIRST", 1);

@@ -239,24 +239,25 @@ size_t tcl_weight_image_bytes() { return tcl::kWBytes; }
 
 // w [cout][64][3][3] fp32 (cout = 4 or 1) -> [kx][32 rows][64 k] fp16, 128-byte swizzle;
 // row n < 16: hi(W[c][k][ky][kx]) with n = ky*cout + c (zero for n >= 3*cout); row 16+n: lo'.
-void tcl_pack_weights(const float* w, int cout, uint8_t* img) {
-  memset(img, 0, tcl::kWBytes);
+template <class Emit>
+static void tcl_layout(int cout, Emit emit) {
   for (int kx = 0; kx < 3; ++kx)
     for (int n = 0; n < 32; ++n) {
       const int nn = n & 15;
       if (nn >= 3 * cout) continue;
       const int ky = nn / cout, c = nn % cout;
       for (int k = 0; k < 64; ++k) {
-        const float v = w[((c * 64 + k) * 3 + ky) * 3 + kx];
-        const __half hi = __float2half_rn(v);
-        __half val = hi;
-        if (n >= 16) val = __float2half_rn((v - __half2float(hi)) * kLoScale);
         const size_t byte = (size_t)kx * tcl::kKxBytesB + (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) +
                             (size_t)(k & 7) * 2;
-        *reinterpret_cast<__half*>(img + byte) = val;
+        emit(byte, ((c * 64 + k) * 3 + ky) * 3 + kx, n >= 16);
       }
     }
 }
+void tcl_pack_weights(const float* w, int cout, uint8_t* img) {
+  memset(img, 0, tcl::kWBytes);
+  tcl_layout(cout, PackWrite{w, img});
+}
+void tcl_pack_map(int cout, int32_t* map) { tcl_layout(cout, PackMap{map}); }
 
 bool tcl_supported(int Wc) {
   static const int enabled = env_int("DEQSCI_TC_LAST", 1);

@@ -25,7 +25,8 @@ Layout layout(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
   L.gram_floats = align_up_sz((size_t)B * m * m, 64);
   L.alpha_floats = align_up_sz((size_t)B * m, 64);
   L.scratch_floats = align_up_sz(deqsci_anderson_scratch_floats(B, m, (long long)N), 64);
-  L.floats_total = L.hist_floats + L.gram_floats + L.alpha_floats + L.scratch_floats + 64 /*res*/;
+  L.floats_total = L.hist_floats + L.gram_floats + L.alpha_floats + L.scratch_floats + 64 /*res*/ +
+                   (size_t)kMaxBnLayers * 2 * kHidden /*running-statistics snapshot*/;
   L.den_bytes = deqsci_denoiser_workspace_bytes(h, B, H, W, T);
   L.total_bytes = 1024 + align_up_sz(L.floats_total * sizeof(float), 1024) + L.den_bytes;
   return L;
@@ -38,10 +39,12 @@ extern "C" size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, i
   return L.den_bytes == 0 ? 0 : L.total_bytes;
 }
 
-extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
-                                  const float* x0, float* out, const deqsci_solver_opts* o, void* workspace,
-                                  size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
-                                  void* stream) {
+namespace {
+// bn == nullptr: eval-mode plan (BatchNorm folded); else train-mode f calls (deqsci_iterate_train)
+int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+                     const float* x0, float* out, const deqsci_solver_opts* o, const deqsci_bn_params* bn,
+                     float momentum, float eps, void* workspace, size_t workspace_bytes,
+                     deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
   DEQSCI_CHECK_ARG(h && y && phi && phi_sum && out && o && workspace && result, "reconstruct: null pointer");
   DEQSCI_CHECK_ARG(o->m >= 2 && o->m <= 8, "reconstruct: m=%d unsupported (2..8)", o->m);
   DEQSCI_CHECK_ARG(o->max_iter >= 2, "reconstruct: max_iter=%d (need >= 2)", o->max_iter);
@@ -64,6 +67,8 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
   float* alpha = gram + L.gram_floats;
   float* scratch = alpha + L.alpha_floats;
   float* res_dev = scratch + L.scratch_floats;
+  float* bn_backup = res_dev + 64;
+  const int n_layers = denoiser_num_layers(h);
   void* den_ws = base + align_up_sz(L.floats_total * sizeof(float), 1024);
   const size_t slot = (size_t)B * N;
   auto Xs = [&](int s) { return X + (size_t)s * slot; };
@@ -77,6 +82,9 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
     sigma_prev = sigma;
     sigma = sigma * o->sigma_decay;
     ++calls;
+    if (bn)
+      return deqsci_iterate_train(h, zin, y, phi, phi_sum, sigma_prev, zout, den_ws, L.den_bytes, bn, momentum, eps, B,
+                                  H, W, T, stream);
     return deqsci_iterate(h, zin, y, phi, phi_sum, sigma_prev, zout, den_ws, L.den_bytes, B, H, W, T, stream);
   };
   auto undo_call = [&]() { sigma = sigma_prev; --calls; };   // a speculative iteration does not advance the schedule
@@ -105,6 +113,8 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
     current_k = k;
     const int n = k < m ? k : m, s = k % m;
     if ((rc = deqsci_anderson_mix(X, F, alpha, B, m, N, s, n, o->beta, stream))) break;
+    // train mode: iteration k may turn out speculative (k > 2) -- keep the running statistics it will update
+    if (bn && k > 2 && (rc = bn_running_snapshot(bn, n_layers, bn_backup, 0, st))) break;
     if ((rc = f_call(Xs(s), Fs(s)))) break;
     if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, s, (k + 1 < m ? k + 1 : m),
                                      o->lam, (float)o->res_eps, stream))) break;
@@ -117,6 +127,7 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
     }
     if (k > 2 && res_of(k - 1) < (double)o->tol) {      // iteration k was speculative
       undo_call();
+      if (bn) rc = bn_running_snapshot(bn, n_layers, bn_backup, 1, st);
       stop_k = current_k = k - 1;
       break;
     }
@@ -141,4 +152,23 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
   result->sigma_next = sigma;
   (void)stop_k;
   return DEQSCI_OK;
+}
+}  // namespace
+
+extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+                                  const float* x0, float* out, const deqsci_solver_opts* o, void* workspace,
+                                  size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
+                                  void* stream) {
+  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, nullptr, 0.f, 0.f, workspace, workspace_bytes, result, B, H,
+                          W, T, stream);
+}
+
+extern "C" int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y, const float* phi,
+                                        const float* phi_sum, const float* x0, float* out,
+                                        const deqsci_solver_opts* o, const deqsci_bn_params* bn, float momentum,
+                                        float eps, void* workspace, size_t workspace_bytes,
+                                        deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(bn != nullptr, "reconstruct_train: null BatchNorm table");
+  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, bn, momentum, eps, workspace, workspace_bytes, result, B, H,
+                          W, T, stream);
 }

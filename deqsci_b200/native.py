@@ -70,6 +70,21 @@ class NativeDenoiser:
         self._rws = None
         self.num_layers = len(layers)
 
+    def update_weights(self, weights):
+        """Refreshes the plan's conv weights from the live device tensors (deqsci_denoiser_update_weights):
+        stream-ordered repack kernels, no host copy -- what a training loop needs after optimizer.step()."""
+        if len(weights) != self.num_layers:
+            raise DeqsciError("update_weights: %d tensors for %d conv layers" % (len(weights), self.num_layers))
+        ptrs = (ctypes.c_void_p * self.num_layers)()
+        for i, w in enumerate(weights):
+            w = _req(w.detach(), "weight %d" % i, 4)
+            self._check_dev(w)
+            ptrs[i] = w.data_ptr()
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_denoiser_update_weights(self._h, self.num_layers, ptrs,
+                                                       torch.cuda.current_stream(self.device).cuda_stream),
+                  "deqsci_denoiser_update_weights")
+
     def _workspace(self, B, H, W, T):
         need = lib().deqsci_denoiser_workspace_bytes(self._h, B, H, W, T)
         if need == 0:
@@ -119,18 +134,9 @@ class NativeDenoiser:
                                        _stream(z)), "deqsci_iterate")
         return out
 
-    def iterate_train(self, z, y, phi, phi_sum, sigma, bn_modules, out=None):
-        """One call of the iterate map with the denoiser in TRAIN mode (deqsci_iterate_train):
-        batch-statistics BatchNorm, running statistics of `bn_modules` updated in place once (momentum,
-        unbiased variance, num_batches_tracked += 1), like nn.BatchNorm2d.  bn_modules[i] is the
-        BatchNorm2d that follows conv layer i of the plan, or None.  The plan must be a train plan
-        (BatchNorm not folded)."""
-        z, y = _req(z, "z", 4), _req(y, "y", 3)
-        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
-        self._check_dev(z)
-        B, H, W, T = (int(s) for s in z.shape)
+    def _bn_table(self, bn_modules):
         if len(bn_modules) != self.num_layers:
-            raise DeqsciError("iterate_train: %d BatchNorm slots for %d conv layers" % (len(bn_modules), self.num_layers))
+            raise DeqsciError("%d BatchNorm slots for %d conv layers" % (len(bn_modules), self.num_layers))
         arr = (_lib.BNParams * self.num_layers)()
         momentum, eps = 0.1, 1e-5
         for i, bn in enumerate(bn_modules):
@@ -143,6 +149,19 @@ class NativeDenoiser:
             arr[i].beta = bn.bias.data_ptr() if bn.affine else None
             arr[i].running_mean = bn.running_mean.data_ptr()
             arr[i].running_var = bn.running_var.data_ptr()
+        return arr, momentum, eps
+
+    def iterate_train(self, z, y, phi, phi_sum, sigma, bn_modules, out=None):
+        """One call of the iterate map with the denoiser in TRAIN mode (deqsci_iterate_train):
+        batch-statistics BatchNorm, running statistics of `bn_modules` updated in place once (momentum,
+        unbiased variance, num_batches_tracked += 1), like nn.BatchNorm2d.  bn_modules[i] is the
+        BatchNorm2d that follows conv layer i of the plan, or None.  The plan must be a train plan
+        (BatchNorm not folded)."""
+        z, y = _req(z, "z", 4), _req(y, "y", 3)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
+        self._check_dev(z)
+        B, H, W, T = (int(s) for s in z.shape)
+        arr, momentum, eps = self._bn_table(bn_modules)
         if out is None:
             out = torch.empty_like(z)
         ws = self._workspace(B, H, W, T)
@@ -156,9 +175,11 @@ class NativeDenoiser:
         return out
 
     def reconstruct(self, y, phi, phi_sum, x0=None, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5,
-                    sigma_start_call=0, final_call=True, sigma0=60 / 255, sigma_decay=0.971):
+                    sigma_start_call=0, final_call=True, sigma0=60 / 255, sigma_decay=0.971, bn_modules=None):
         """Whole DE-GAP reconstruction in ONE C-ABI call (deqsci_reconstruct): andersonexp on the
-        iterate map + the final f call.  Returns (out [B,H,W,T], SolverResult)."""
+        iterate map + the final f call.  Returns (out [B,H,W,T], SolverResult).  bn_modules (train
+        plans only): the solve runs with batch-statistics BatchNorm (deqsci_reconstruct_train) and
+        updates the modules' running statistics / num_batches_tracked once per counted f call."""
         y = _req(y, "y", 3)
         phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), y), _bcast_phi(_req(phi_sum, "Phi_sum", 3), y)
         self._check_dev(y)
@@ -179,10 +200,21 @@ class NativeDenoiser:
                                float(sigma_decay), int(sigma_start_call), int(bool(final_call)), 1e-5)
         res = _lib.SolverResult()
         with torch.cuda.device(self.device):
-            check(lib().deqsci_reconstruct(self._h, y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
-                                           x0.data_ptr() if x0 is not None else None, out.data_ptr(),
-                                           ctypes.byref(opts), self._rws.data_ptr(), self._rws.numel(),
-                                           ctypes.byref(res), B, H, W, T, _stream(y)), "deqsci_reconstruct")
+            if bn_modules is None:
+                check(lib().deqsci_reconstruct(self._h, y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                               x0.data_ptr() if x0 is not None else None, out.data_ptr(),
+                                               ctypes.byref(opts), self._rws.data_ptr(), self._rws.numel(),
+                                               ctypes.byref(res), B, H, W, T, _stream(y)), "deqsci_reconstruct")
+            else:
+                arr, momentum, eps = self._bn_table(bn_modules)
+                check(lib().deqsci_reconstruct_train(self._h, y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                                     x0.data_ptr() if x0 is not None else None, out.data_ptr(),
+                                                     ctypes.byref(opts), arr, momentum, eps, self._rws.data_ptr(),
+                                                     self._rws.numel(), ctypes.byref(res), B, H, W, T, _stream(y)),
+                      "deqsci_reconstruct_train")
+                for bn in bn_modules:
+                    if bn is not None and bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked += int(res.f_calls)
         return out, res
 
     def debug_hidden_layer(self, layer, act_in, NF, Hc, Wc):
@@ -195,12 +227,28 @@ class NativeDenoiser:
         return out
 
 
+class _PlanStore(dict):
+    """Per-module plan cache; plans hold device handles, so copy.deepcopy / pickle / torch.save(module)
+    carry an empty store instead."""
+
+    def __deepcopy__(self, memo):
+        return _PlanStore()
+
+    def __reduce__(self):
+        return (_PlanStore, ())
+
+
 class NativePlanCache:
     """Mixin for the nn.Module mirrors: builds / caches a NativeDenoiser per (device, precision)
     and rebuilds it when any parameter or buffer changed (tensor version counters)."""
 
     def _plan_layers(self, train=False):  # -> (kind, [layer dicts]); train=True: BatchNorm NOT folded
         raise NotImplementedError
+
+    def _plan_live_weights(self, train=False):
+        """The conv weight tensors a plan can be refreshed from on the device (same order as the plan's
+        layers), or None when the plan holds anything derived on the host (folded BatchNorm, spectral norm)."""
+        return None
 
     def _plan_signature(self, train=False):
         # the train plan holds conv weights only: running statistics change on every call and must not
@@ -214,11 +262,17 @@ class NativePlanCache:
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        cache = self.__dict__.setdefault("_native_cache", {})
+        cache = self.__dict__.setdefault("_native_cache", _PlanStore())
         key = (str(device), precision, bool(train))
         sig = self._plan_signature(train)
         hit = cache.get(key)
         if hit is None or hit[0] != sig:
-            kind, layers = self._plan_layers(train) if train else self._plan_layers()
-            cache[key] = (sig, NativeDenoiser(kind, layers, precision, device))
+            live = self._plan_live_weights(train)
+            ident = None if live is None else tuple((id(t), t.data_ptr(), tuple(t.shape)) for t in live)
+            if hit is not None and ident is not None and hit[2] == ident and all(t.device == device for t in live):
+                hit[1].update_weights(live)       # same tensors, new values (an optimizer step): repack on the device
+                cache[key] = (sig, hit[1], ident)
+            else:
+                kind, layers = self._plan_layers(train) if train else self._plan_layers()
+                cache[key] = (sig, NativeDenoiser(kind, layers, precision, device), ident)
         return cache[key][1]

@@ -89,6 +89,20 @@ def sequential_to_plan_layers(seq, fold_bn=True):
     return layers
 
 
+def sequential_live_weights(seq, train):
+    """Conv weights of a plain Conv2d / BatchNorm2d / ReLU stack, for the device-side plan refresh; None
+    when the plan also depends on host-folded BatchNorm (eval plans of stacks with BatchNorm) or on
+    derived weights (spectral norm)."""
+    if not all(isinstance(m, (nn.Conv2d, nn.BatchNorm2d, nn.ReLU)) for m in seq):
+        return None
+    if any(hasattr(m, "plan_weight") or hasattr(m, "weight_orig") for m in seq):
+        return None
+    if not train and any(isinstance(m, nn.BatchNorm2d) for m in seq):
+        return None
+    ws = [m.weight for m in seq if isinstance(m, nn.Conv2d)]
+    return ws if all(w.dtype == torch.float32 and w.is_contiguous() for w in ws) else None
+
+
 class FFDNet(nn.Module, NativePlanCache):
     """FFDNet(num_input_channels, tag); forward(x [N,C,H,W], noise_sigma [N]) -> predicted noise.
     The input is detached before the network, as in the reference (models.py:103-104)."""
@@ -118,6 +132,9 @@ class FFDNet(nn.Module, NativePlanCache):
 
     def bn_slots(self):
         return sequential_bn_slots(self.intermediate_dncnn.itermediate_dncnn)
+
+    def _plan_live_weights(self, train=False):
+        return sequential_live_weights(self.intermediate_dncnn.itermediate_dncnn, train)
 
     def native_train_ok(self, z):
         """Train-mode forward solve (no_grad) on the native kernels: cube [B,H,W,T] whose half-resolution

@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ...._lib import DeqsciError
 from ....native import NativePlanCache
-from ...ffdnet.models import sequential_bn_slots, sequential_to_plan_layers
+from ...ffdnet.models import sequential_bn_slots, sequential_live_weights, sequential_to_plan_layers
 from .conv_sn_chen import conv_spectral_norm
 
 
@@ -45,6 +45,9 @@ class DnCNN(nn.Module, NativePlanCache):
 
     def bn_slots(self):
         return sequential_bn_slots(self.dncnn)
+
+    def _plan_live_weights(self, train=False):
+        return sequential_live_weights(self.dncnn, train)
 
     def native_train_ok(self, z):
         """Train-mode forward solve (no_grad) with BatchNorm on the native kernels (plain conv / BatchNorm /

@@ -173,13 +173,19 @@ def forward_iteration(f, x0, max_iter=50, tol=1e-5):
     return f0, res
 
 
+def _train_mode_batchnorm(op):
+    return (op is not None and op.training
+            and any(isinstance(mod, nn.modules.batchnorm._BatchNorm) for mod in op.modules()))
+
+
 class _BoundIterate:
     """f(z) = self.f(z, x, Phi, Phi_sum) with optional in-place output (history slots)."""
 
     def __init__(self, f, x, Phi, Phi_sum):
         self.f, self.x, self.Phi, self.Phi_sum = f, x, Phi, Phi_sum
         self.supports_out = hasattr(f, "_native_ok")
-        self.supports_rollback = hasattr(f, "rollback_call")
+        # a speculative call in train mode would leave a BatchNorm running-statistics update behind
+        self.supports_rollback = hasattr(f, "rollback_call") and not _train_mode_batchnorm(getattr(f, "nonlinear_op", None))
 
     def rollback(self):
         self.f.rollback_call()
@@ -209,46 +215,68 @@ class DEQFixedPoint(nn.Module):
         op = getattr(self.f, "nonlinear_op", None)
         return (not torch.is_grad_enabled()) or (op is not None and not op.training)
 
-    # ---- device-resident driver: the whole inference forward() as one C-ABI call --------------------
-    def _driver_ok(self, z):
+    # ---- device-resident driver: the whole solve (+ the final f call at inference) as one C-ABI call ---
+    def _driver_mode(self, z):
+        """None, "eval" (folded-BatchNorm plan) or "train" (batch-statistics plan), for the no_grad solve."""
         import os
         f = self.f
-        return (os.environ.get("DEQSCI_DRIVER", "1") != "0" and self.solver is andersonexp
-                and hasattr(f, "_native_ok") and f._native_ok(z)
-                and f.A is cg_utils.A_torch_ and f.At is cg_utils.At_torch_
+        if not (os.environ.get("DEQSCI_DRIVER", "1") != "0" and self.solver is andersonexp
+                and hasattr(f, "_native_ok") and getattr(f, "A", None) is cg_utils.A_torch_
+                and getattr(f, "At", None) is cg_utils.At_torch_
                 and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"} and self.kwargs.get("max_iter", 50) >= 2
-                and not f._forward_pre_hooks and not f._forward_hooks)
+                and not f._forward_pre_hooks and not f._forward_hooks):
+            return None
+        with torch.no_grad():
+            if f._native_ok(z):
+                return "eval"
+            op = f.nonlinear_op
+            if op.tag in ('ffdnet', 'denoiser') and getattr(op, "native_train_ok", lambda t: False)(z):
+                return "train"
+        return None
 
-    def _forward_driver(self, x, Phi, Phi_sum, init_point):
+    def _driver_ok(self, z):
+        return self._driver_mode(z) is not None
+
+    def _forward_driver(self, x, Phi, Phi_sum, init_point, final_call=True, mode="eval"):
         f = self.f
+        op = f.nonlinear_op
         start = 0
-        if f.nonlinear_op.tag == 'ffdnet':
+        if op.tag == 'ffdnet':
             f.n_sigma_frames = int(init_point.shape[0] * init_point.shape[3])
             # reset-or-continue decision of the first call; a schedule that was never reset (measurement
             # mean equal to the initial 0) decays its initial 60/255 before first use, as in the reference
             start = 0 if f._observe(x) else max(f._n, 1)
         kw = dict(m=5, lam=1e-4, max_iter=50, tol=1e-5, beta=1.0)
         kw.update(self.kwargs)
-        plan = f.nonlinear_op.native_plan(init_point.device)
-        z, r = plan.reconstruct(x, Phi, Phi_sum, x0=init_point, sigma_start_call=start, final_call=True, **kw)
+        plan = op.native_plan(init_point.device, train=(mode == "train"))
+        z, r = plan.reconstruct(x, Phi, Phi_sum, x0=init_point, sigma_start_call=start, final_call=final_call,
+                                bn_modules=op.bn_slots() if mode == "train" else None, **kw)
         self.forward_res = float(r.residual)
-        if f.nonlinear_op.tag == 'ffdnet':
-            f._n = start + int(r.f_calls) + 1              # + the reference's second post-solver call
+        if op.tag == 'ffdnet':
+            # inference: + the reference's second post-solver call, which is skipped
+            f._n = start + int(r.f_calls) + (1 if final_call else 0)
             f._undo = None
         return z
 
     def forward(self, x, Phi, Phi_sum, initial_point=None, train_flag=True):
         init_point = torch.zeros_like(Phi.expand(x.shape[0], *Phi.shape[1:])) if initial_point is None else initial_point
         bound = _BoundIterate(self.f, x, Phi, Phi_sum)
-        if self._inference() and self._driver_ok(init_point):
-            return self._forward_driver(x, Phi, Phi_sum, init_point)
-        with torch.no_grad():
-            z, self.forward_res = self.solver(bound, init_point, **self.kwargs)
-        if self._inference():
+        mode = self._driver_mode(init_point)
+        inference = self._inference()
+        if inference and mode == "eval":
+            return self._forward_driver(x, Phi, Phi_sum, init_point, True, mode)
+        if mode is not None:           # the no_grad solve on the driver; the post-solver calls follow below
+            z = self._forward_driver(x, Phi, Phi_sum, init_point, False, mode)
+        else:
+            with torch.no_grad():
+                z, self.forward_res = self.solver(bound, init_point, **self.kwargs)
+        if inference:
             with torch.no_grad():
                 z = bound(z)
-            if hasattr(self.f, "skip_call"):
-                self.f.skip_call()
+                if _train_mode_batchnorm(getattr(self.f, "nonlinear_op", None)):
+                    bound(z)           # the reference's second call: kept for its running-statistics update
+                elif hasattr(self.f, "skip_call"):
+                    self.f.skip_call()
             return z
         z = self.f(z, x, Phi, Phi_sum)
         # tag 'ffdnet': the denoiser sees x.data, so the Jacobian of f w.r.t. z is the GAP projector and

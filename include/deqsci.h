@@ -103,6 +103,14 @@ int deqsci_denoiser_create(int net_kind, int precision, int num_layers,
                            const deqsci_conv_layer* layers_host, deqsci_denoiser** out);
 int deqsci_denoiser_destroy(deqsci_denoiser* h);
 
+/* Refreshes the conv weights of an existing plan from DEVICE tensors (fp32 [cout][cin][3][3] each, e.g.
+ * the parameters an optimizer step just updated in place), stream-ordered on `stream`: no host round
+ * trip, no synchronisation, no allocation after the first call (which builds the gather maps).  Folded
+ * scale/bias are left as they are, so this is for plans whose BatchNorm is not folded (train plans) or
+ * absent.  The caller orders it against launches that use the plan on other streams. */
+int deqsci_denoiser_update_weights(deqsci_denoiser* h, int num_layers, const float* const* weight_dev,
+                                   void* stream);
+
 /* Bytes of scratch (activation ping-pong planes) for a [B,H,W,T] cube. */
 size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
 
@@ -213,6 +221,17 @@ int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, const float* ph
                        const float* x0, float* out, const deqsci_solver_opts* opts,
                        void* workspace, size_t workspace_bytes, deqsci_solver_result* result,
                        int B, int H, int W, int T, void* stream);
+
+/* The same loop with the denoiser in TRAIN mode (every f call = deqsci_iterate_train): the no_grad
+ * forward solve DEQFixedPoint.forward runs while training (solvers/new_equilibrium_utils_yaping.py:265-266).
+ * `h` must be a train plan, `bn` as for deqsci_iterate_train; running statistics receive one momentum
+ * update per counted f call (result->f_calls; a speculative iteration's update is rolled back).
+ * Normally called with opts->final_call = 0: the caller's graph-attached f(z*) follows. */
+int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+                             const float* x0, float* out, const deqsci_solver_opts* opts,
+                             const deqsci_bn_params* bn, float momentum, float eps,
+                             void* workspace, size_t workspace_bytes, deqsci_solver_result* result,
+                             int B, int H, int W, int T, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Launch accounting and sampled device timing of the library's own kernels.

@@ -58,7 +58,7 @@ def test_training_step_gradients_vs_reference(train_vectors, train_wide_vectors,
             else:
                 assert rel_l2(got_b, v[k]) <= 1e-3, k
     assert rel_l2(rec.detach().cpu().numpy(), v["rec_" + d]) <= 1e-3
-    assert abs(float(loss) - float(v["loss_" + d])) <= 1e-3 * float(v["loss_" + d])
+    assert abs(float(loss.detach()) - float(v["loss_" + d])) <= 1e-3 * float(v["loss_" + d])
     assert abs(deq.forward_res - float(v["fres_" + d])) <= 1e-2 * float(v["fres_" + d])
     assert abs(deq.backward_res - float(v["bres_" + d])) <= 1e-2 * float(v["bres_" + d])
     names = [str(n) for n in v["gradnames_" + d]]
@@ -131,3 +131,65 @@ def test_train_mode_batchnorm_native_vs_torch(kind):
         assert rel_l2(ma.running_var.cpu().numpy(), mb.running_var.cpu().numpy()) <= 1e-4
     if kind == "ffdnet":
         assert a._n == b._n == 2
+
+
+@pytest.mark.parametrize("d", ["SimpleCNN", "ffdnet"])
+def test_train_driver_equals_python_loop(train_wide_vectors, d, monkeypatch):
+    """The training forward solve through deqsci_reconstruct(_train) (one C-ABI call) and through the
+    Python andersonexp loop queue the same kernels: reconstruction, gradients, BatchNorm running
+    statistics, num_batches_tracked and the sigma call counter are identical."""
+    dev = torch.device("cuda", 0)
+    out = {}
+    for driver in ("1", "0"):
+        monkeypatch.setenv("DEQSCI_DRIVER", driver)
+        solver, deq, rec, loss = _step(d, train_wide_vectors, dev)
+        out[driver] = (rec.detach().clone(), {k: p.grad.clone() for k, p in solver.named_parameters() if p.grad is not None},
+                       {k: b.clone() for k, b in solver.named_buffers()}, getattr(solver, "_n", None), deq.forward_res)
+    a, b = out["1"], out["0"]
+    assert torch.equal(a[0], b[0])
+    # gradients come out of cuDNN's backward kernels (atomics): equal up to their run-to-run noise
+    assert a[1].keys() == b[1].keys()
+    for k in a[1]:
+        assert rel_l2(a[1][k].cpu().numpy(), b[1][k].cpu().numpy()) <= 1e-5, k
+    assert all(torch.equal(a[2][k], b[2][k]) for k in a[2])
+    assert a[3] == b[3]
+    assert a[4] == b[4]
+
+
+@pytest.mark.parametrize("d", ["SimpleCNN", "ffdnet"])
+def test_plan_refresh_on_device_equals_rebuild(d):
+    """After an in-place parameter update (optimizer.step()) the cached plan is refreshed by the repack
+    kernels (deqsci_denoiser_update_weights) -- same object, no host copy -- and computes exactly what a
+    plan packed on the host from the new weights computes."""
+    import copy
+    from test_gpu_parity import build_solver
+    dev = torch.device("cuda", 0)
+    solver = build_solver(d, dev)
+    op = solver.nonlinear_op
+    train = d == "ffdnet"                   # FFDNet: the train plan (BatchNorm not folded) is the refreshable one
+    g = torch.Generator(device="cpu").manual_seed(5)
+    z = torch.rand(2, 32, 160, 8, generator=g).to(dev)
+    y = torch.rand(2, 32, 160, generator=g).to(dev) * 4
+    Phi = (torch.rand(2, 32, 160, 8, generator=g) > 0.5).float().to(dev)
+    Ps = Phi.sum(3)
+    Ps[Ps == 0] = 1
+
+    def run(mod, plan):
+        if train:
+            return plan.iterate_train(z, y, Phi, Ps, 0.2, mod.bn_slots())
+        return plan.iterate(z, y, Phi, Ps, 0.0)
+
+    plan0 = op.native_plan(dev, train=train)
+    before = run(op, plan0)
+    with torch.no_grad():
+        for i, p in enumerate(op.parameters()):
+            p.mul_(1.0 + 0.01 * ((i % 3) - 1)).add_(1e-3)
+    fresh = copy.deepcopy(op)               # identical weights and buffers, no cached plan: packed on the host
+    assert not fresh.__dict__.get("_native_cache")
+    plan1 = op.native_plan(dev, train=train)
+    assert plan1 is plan0                   # refreshed in place
+    got = run(op, plan1)
+    want = run(fresh, fresh.native_plan(dev, train=train))
+    assert fresh.native_plan(dev, train=train) is not plan0
+    assert torch.equal(got, want)
+    assert not torch.equal(got, before)
