@@ -59,7 +59,8 @@ bool tc2_supported(int Hc, int Wc);
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                             cudaStream_t st, double* stats = nullptr);
-int bn_train_launch(__half* act, long long plane_elems, double* stats, float* scale_shift, const float* gamma,
+int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift,
+                    const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     long long count, int relu, cudaStream_t st);
 size_t tc_weight_image_bytes(bool split, int cout);
@@ -90,6 +91,10 @@ struct deqsci_denoiser {
 using namespace deqsci;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// train-mode BatchNorm scratch at the end of the workspace: per-CTA statistics partials + scale/shift
+constexpr int kMaxStatCtas = 256;
+constexpr size_t kTrainScratchBytes = (size_t)kMaxStatCtas * 2 * kHidden * sizeof(double) + 1024;
 
 int deqsci::denoiser_num_layers(const deqsci_denoiser* h) { return h ? (int)h->layers.size() : 0; }
 
@@ -305,7 +310,7 @@ int geometry(const deqsci_denoiser* h, int B, int H, int W, int T, Geometry* g) 
 extern "C" size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T) {
   Geometry g;
   if (geometry(h, B, H, W, T, &g) != DEQSCI_OK) return 0;
-  return 1024 + g.zprime_bytes + 2 * g.act_bytes + 4096 /* train-mode BatchNorm statistics */;
+  return 1024 + g.zprime_bytes + 2 * g.act_bytes + kTrainScratchBytes;
 }
 
 static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, const float* y, const float* phi,
@@ -318,7 +323,7 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   DEQSCI_CHECK_ARG(z != nullptr && out != nullptr && workspace != nullptr, "null pointer");
   if (fuse_gap) DEQSCI_CHECK_ARG(y && phi && phi_sum, "iterate: null y / phi / phi_sum");
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-  const size_t need = (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + g.zprime_bytes + 2 * g.act_bytes + 4096;
+  const size_t need = (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + g.zprime_bytes + 2 * g.act_bytes + kTrainScratchBytes;
   if (workspace_bytes < need) {
     set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     return DEQSCI_ERR_WORKSPACE;
@@ -328,13 +333,15 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
                     reinterpret_cast<__half*>(ws + g.zprime_bytes + g.act_bytes)};
   cudaStream_t st = (cudaStream_t)stream;
   const int nl = (int)h->layers.size();
-  double* bn_stats = reinterpret_cast<double*>(ws + g.zprime_bytes + 2 * g.act_bytes);      // [128]
-  float* bn_scale_shift = reinterpret_cast<float*>(bn_stats + 2 * kHidden);                  // [128]
+  double* bn_stats = reinterpret_cast<double*>(ws + g.zprime_bytes + 2 * g.act_bytes);      // [kMaxStatCtas][128]
+  float* bn_scale_shift = reinterpret_cast<float*>(bn_stats + (size_t)kMaxStatCtas * 2 * kHidden);   // [128]
   if (bn) {
     DEQSCI_CHECK_ARG(h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc) && tcf_supported(g.Wc),
                      "train-mode BatchNorm path needs precision tc_split and conv images wider than 64 with even "
                      "height (got %dx%d)", g.Hc, g.Wc);
-    DEQSCI_CUDA(cudaMemsetAsync(bn_stats, 0, 2 * kHidden * sizeof(double), st));
+    DEQSCI_CHECK_ARG(num_sms() <= kMaxStatCtas, "train-mode BatchNorm path: %d SMs (max %d)", num_sms(), kMaxStatCtas);
+    // rows of CTAs a launch does not start stay zero (every hidden layer of this call uses the same grid)
+    DEQSCI_CUDA(cudaMemsetAsync(bn_stats, 0, (size_t)kMaxStatCtas * 2 * kHidden * sizeof(double), st));
   }
   const Layer& L0 = h->layers[0];
   if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
@@ -361,7 +368,7 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
       rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
                                    g.Wc, st, bn_stats);
       if (rc == DEQSCI_OK)
-        rc = bn_train_launch(act[cur ^ 1], g.plane_elems, bn_stats, bn_scale_shift, bn[i].gamma, bn[i].beta,
+        rc = bn_train_launch(act[cur ^ 1], g.plane_elems, bn_stats, num_sms(), bn_scale_shift, bn[i].gamma, bn[i].beta,
                              bn[i].running_mean, bn[i].running_var, momentum, eps, (long long)g.NF * g.Hc * g.Wc,
                              L.relu, st);
     } else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))

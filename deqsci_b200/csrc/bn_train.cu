@@ -1,22 +1,38 @@
 // Train-mode BatchNorm2d for the hidden conv layers (nn.BatchNorm2d(64), eps 1e-5, momentum 0.1,
 // networks/ffdnet/models.py:58): batch statistics over (frames, H, W) per channel.
-//   bn_finalize : from the per-channel sum / sum of squares the conv kernel accumulated (fp64):
+//   bn_finalize : adds up the per-CTA partial sums / sums of squares the conv kernel wrote (fp64, fixed order):
 //                 mean, biased variance -> scale = gamma * rsqrt(var + eps), shift = beta - mean*scale;
-//                 running_mean / running_var momentum update (unbiased variance), accumulators re-zeroed
+//                 running_mean / running_var momentum update (unbiased variance)
 //   bn_apply    : y = relu(x * scale[c] + shift[c]) on the raw conv output planes, in place
 //                 (fp16 hi/lo pair -> fp32 -> affine -> re-split); 256 B per pixel read + written.
 #include "common.cuh"
 
 namespace deqsci {
 
-__global__ void bn_finalize_kernel(double* __restrict__ stats, float* __restrict__ scale_shift,
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_partials, float* __restrict__ scale_shift,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, double count) {
-  const int c = threadIdx.x;
+  // 1024 threads: 8 row groups x 128 columns of the per-CTA partials; every column is added up in a fixed
+  // order (group-strided rows, then the 8 groups), so the statistics are deterministic
+  __shared__ double part[8][2 * kHidden];
+  __shared__ double tot[2 * kHidden];
+  const int t = threadIdx.x & (2 * kHidden - 1), grp = threadIdx.x >> 7;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int k = grp; k < n_partials; k += 8) acc += stats[(size_t)k * 2 * kHidden + t];
+  part[grp][t] = acc;
+  __syncthreads();
+  if (grp != 0) return;
+  acc = 0.0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) acc += part[g][t];
+  tot[t] = acc;
+  __syncthreads();
+  const int c = t;
   if (c >= kHidden) return;
-  const double mean = stats[c] / count;
-  double var = stats[kHidden + c] / count - mean * mean;
+  const double mean = tot[c] / count;
+  double var = tot[kHidden + c] / count - mean * mean;
   if (var < 0.0) var = 0.0;
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float sc = g * rsqrtf((float)var + eps);
@@ -27,8 +43,6 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, float* __restrict
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
-  stats[c] = 0.0;
-  stats[kHidden + c] = 0.0;
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act, long long plane_elems,
@@ -55,12 +69,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act,
   }
 }
 
-// stats: device double[128] (zero on entry, zero again on exit); scale_shift: device float[128] scratch
-int bn_train_launch(__half* act, long long plane_elems, double* stats, float* scale_shift, const float* gamma,
+// stats: device double[n_partials][128], the conv kernel's per-CTA partial sums (rows of CTAs that did not
+// run are zero); scale_shift: device float[128] scratch
+int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     long long count, int relu, cudaStream_t st) {
-  bn_finalize_kernel<<<1, kHidden, 0, st>>>(stats, scale_shift, gamma, beta, running_mean, running_var, momentum, eps,
-                                            (double)count);
+  bn_finalize_kernel<<<1, 8 * 2 * kHidden, 0, st>>>(stats, n_partials, scale_shift, gamma, beta, running_mean, running_var,
+                                                momentum, eps, (double)count);
   DEQSCI_LAUNCH_CHECK();
   long long blocks = (plane_elems / 8 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;

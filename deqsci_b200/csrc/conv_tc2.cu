@@ -114,7 +114,7 @@ struct Params {
   int tiles_x, strips_y, strip_rows;
   long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
   long long n_pair_items;
-  double* stats;              // STATS kernels: [128] = per-channel sum, then sum of squares
+  double* stats;              // STATS kernels: [gridDim.x][128] per-CTA partials: channel sums, then sums of squares
   int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
   __half* dbg_out_hi;
   __half* dbg_out_lo;
@@ -136,7 +136,7 @@ __device__ __forceinline__ Strip decode(const Params& p, long long strip) {
 }
 
 // STATS = true (train-mode BatchNorm): additionally accumulates per-output-channel sum and sum of
-// squares of the values it writes (over valid pixels) into p.stats[0..63] / [64..127] (fp64 atomics).
+// squares of the values it writes (over valid pixels); every CTA writes its partial to p.stats[cta][128].
 template <bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
@@ -357,6 +357,9 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     }
     if (lane == 0) bulk_wait0();
     if (STATS) {
+      // warp totals of this warp's 32 channels -> its (now idle) staging buffer: [0,32) sums, [32,64) squares
+      float* mine = reinterpret_cast<float*>(st_s + e * kStageBytes);
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         float a = st_sum[c], b = st_sq[c];
@@ -366,14 +369,25 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
           b += __shfl_xor_sync(0xffffffffu, b, o);
         }
         if (lane == 0) {
-          atomicAdd(p.stats + half * 32 + c, (double)a);
-          atomicAdd(p.stats + 64 + half * 32 + c, (double)b);
+          mine[c] = a;
+          mine[32 + c] = b;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (STATS && threadIdx.x < 2 * 64) {
+    // CTA partial in a fixed summation order (deterministic): p.stats[cta][0..63] sums, [64..127] sums of
+    // squares; the finalize kernel adds the CTAs up in fp64.  No atomics: all CTAs finish together, and
+    // ~600 same-address fp64 atomics per channel cost 20 us per launch.
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63, half = c >> 5;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      acc += (double)reinterpret_cast<const float*>(st_s + (half * 4 + q) * kStageBytes)[which * 32 + (c & 31)];
+    p.stats[(size_t)blockIdx.x * 128 + threadIdx.x] = acc;
+  }
   cluster_sync();                 // the peer may still be reading this CTA's weights / barriers until here
   if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
 }
