@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <utility>
 
 #include "../../include/deqsci.h"
 
@@ -56,6 +57,30 @@ struct ProfScope {
   cudaStream_t st_;
   long long idx_;
 };
+
+int env_int(const char* name, int dflt);
+
+// Launch with programmatic stream serialization (PDL): the kernel may start while its stream predecessor is
+// still draining.  Only for kernels that execute `griddepcontrol.wait` before touching anything the
+// predecessor wrote.  DEQSCI_TC_PDL=0 falls back to plain stream order.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  static const int pdl = env_int("DEQSCI_TC_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // tma_host.cu
 int make_plane_map(::CUtensorMap_st* map, const __half* plane, int channels, int NF, int Hc, int Wc, int box_c,

@@ -154,7 +154,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 
   // programmatic dependent launch: the next layer's CTAs may take over each SM as soon as this grid's CTA
   // leaves it and run their prologue (barriers, TMEM, 72 KB of weights) under this grid's tail
-  asm volatile("griddepcontrol.launch_dependents;");
+  pdl_launch_dependents();
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,7 +196,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     if (elect_one_sync()) {
       // the activations are the previous kernel's output: wait for that grid to complete (its memory is then
       // visible).  Everything this kernel writes depends on these loads, so no other thread needs the wait.
-      asm volatile("griddepcontrol.wait;" ::: "memory");
+      pdl_wait_predecessor();
       int slot = 0;
       uint32_t phase = 0;
       for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
@@ -459,26 +459,16 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
   ProfScope prof(PK_CONV_HIDDEN, st);
-  // launched with programmatic stream serialization (DEQSCI_TC_PDL=0 disables): see griddepcontrol in the kernel
-  static const int pdl = env_int("DEQSCI_TC_PDL", 1);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * pairs));
-  cfg.blockDim = dim3(tc2::kThreads);
-  cfg.dynamicSmemBytes = tc2::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
   if (stats) {
     DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tc2::kSmemBytes));
-    DEQSCI_CUDA(cudaLaunchKernelEx(&cfg, tc2::conv_hidden_2cta_kernel<true>, in_hi, in_lo, out_hi, out_lo, p));
+    DEQSCI_CUDA(launch_pdl(tc2::conv_hidden_2cta_kernel<true>, (unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st,
+                           in_hi, in_lo, out_hi, out_lo, p));
   } else {
     DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tc2::kSmemBytes));
-    DEQSCI_CUDA(cudaLaunchKernelEx(&cfg, tc2::conv_hidden_2cta_kernel<false>, in_hi, in_lo, out_hi, out_lo, p));
+    DEQSCI_CUDA(launch_pdl(tc2::conv_hidden_2cta_kernel<false>, (unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st,
+                           in_hi, in_lo, out_hi, out_lo, p));
   }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;

@@ -71,6 +71,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0] w, full[S], empty[S], tfull[2], tempty[2]
   float* aff_s = reinterpret_cast<float*>(tail + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+  pdl_launch_dependents();       // the next kernel's prologue may overlap this grid's tail (see conv_tc2.cu)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_w = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
@@ -100,6 +101,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_w, kWBytes);
       bulk_load_1d(smem_u32(w_s), p.wimg, kWBytes, bar_w);
+      pdl_wait_predecessor();      // the input planes are the previous kernel's output
       int slot = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -288,7 +290,8 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    tcf::kSmemBytes));
   ProfScope prof(PK_CONV_FIRST, st);
-  tcf::conv_first_tc_kernel<<<grid, tcf::kThreads, tcf::kSmemBytes, st>>>(in_hi, in_lo, out_hi, out_lo, p);
+  DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi, in_lo, out_hi,
+                         out_lo, p));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }

@@ -84,6 +84,7 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0] w, full[S], empty[S], tfull[4], tempty[4]
   float* aff_s = reinterpret_cast<float*>(tail + 256);         // scale[4], bias[4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 512);
+  pdl_launch_dependents();       // the next kernel's prologue may overlap this grid's tail (see conv_tc2.cu)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_w = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
@@ -114,6 +115,7 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_w, kWBytes);
       bulk_load_1d(smem_u32(w_s), p.wimg, kWBytes, bar_w);
+      pdl_wait_predecessor();      // the input planes are the previous kernel's output
       int slot = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -166,6 +168,7 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
     }
   } else {
     // ===================== epilogue: out row j = V_j[ky=0] + V_{j+1}[ky=1] + V_{j+2}[ky=2]
+    pdl_wait_predecessor();      // z' is read below without passing through the loader's wait
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -285,11 +288,11 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   if (cout == 4) {
     DEQSCI_CUDA(cudaFuncSetAttribute(tcl::conv_last_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tcl::kSmemBytes));
-    tcl::conv_last_tc_kernel<4><<<grid, tcl::kThreads, tcl::kSmemBytes, st>>>(in_hi, in_lo, p);
+    DEQSCI_CUDA(launch_pdl(tcl::conv_last_tc_kernel<4>, (unsigned)grid, tcl::kThreads, tcl::kSmemBytes, st, in_hi, in_lo, p));
   } else {
     DEQSCI_CUDA(cudaFuncSetAttribute(tcl::conv_last_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tcl::kSmemBytes));
-    tcl::conv_last_tc_kernel<1><<<grid, tcl::kThreads, tcl::kSmemBytes, st>>>(in_hi, in_lo, p);
+    DEQSCI_CUDA(launch_pdl(tcl::conv_last_tc_kernel<1>, (unsigned)grid, tcl::kThreads, tcl::kSmemBytes, st, in_hi, in_lo, p));
   }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
