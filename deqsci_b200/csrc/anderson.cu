@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kGramThreads) anderson_gram_kernel(const float
                                                                      float* __restrict__ G,
                                                                      float* __restrict__ partials, int B,
                                                                      long long N, int slot, int n) {
+  pdl_launch_dependents();       // launched with programmatic stream serialization: see launch_pdl (common.cuh)
+  pdl_wait_predecessor();
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
   const long long sstride = (long long)B * N;          // history is slot-major: [m][B][N]
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(1024) anderson_solve_kernel(const float* __res
                                                               float* __restrict__ res, int B, int m, int chunks,
                                                               int slot, int n, float lam, float res_eps,
                                                               int do_solve) {
+  pdl_launch_dependents();
+  pdl_wait_predecessor();
   __shared__ double s_g2[32], s_f2[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double g2 = 0.0, f2 = 0.0;   // per-warp running sums over its samples (fixed order)
@@ -233,6 +237,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) anderson_mix_kernel(float* __restrict__ X, const float* __restrict__ F,
                                                            const float* __restrict__ alpha, int B, int m,
                                                            long long N, int slot, int n, float beta) {
+  pdl_launch_dependents();
+  pdl_wait_predecessor();
   const int b = blockIdx.y;
   const long long sstride = (long long)B * N;          // history is slot-major: [m][B][N]
   float a[kMaxM];
@@ -308,14 +314,15 @@ extern "C" int deqsci_anderson_update(const float* X, const float* F, float* G, 
   {
   ProfScope prof(PK_AND_GRAM, st);
   if (vec4_ok(X, N) && vec4_ok(F, N) && vec4_ok(G, N))
-    anderson_gram_kernel<4, true><<<grid, kGramThreads, 0, st>>>(X, F, G, scratch, B, N, slot, n);
+    DEQSCI_CUDA(launch_pdl(anderson_gram_kernel<4, true>, grid, kGramThreads, 0, st, X, F, G, scratch, B, N, slot, n));
   else
-    anderson_gram_kernel<1, true><<<grid, kGramThreads, 0, st>>>(X, F, G, scratch, B, N, slot, n);
+    DEQSCI_CUDA(launch_pdl(anderson_gram_kernel<1, true>, grid, kGramThreads, 0, st, X, F, G, scratch, B, N, slot, n));
   }
   DEQSCI_LAUNCH_CHECK();
   ProfScope prof2(PK_AND_SOLVE, st);
   int threads = 32 * (B < 32 ? B : 32);
-  anderson_solve_kernel<<<1, threads, 0, st>>>(scratch, gram, alpha, res, B, m, chunks, slot, n, lam, res_eps, 1);
+  DEQSCI_CUDA(launch_pdl(anderson_solve_kernel, 1, threads, 0, st, (const float*)scratch, gram, alpha, res, B, m, chunks, slot, n,
+                         lam, res_eps, 1));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }
@@ -335,8 +342,8 @@ extern "C" int deqsci_anderson_mix(float* X, const float* F, const float* alpha,
   if (bx > 65535) bx = 65535;
   dim3 grid((unsigned)bx, B);
   ProfScope prof(PK_AND_MIX, st);
-  if (v4) anderson_mix_kernel<4><<<grid, threads, 0, st>>>(X, F, alpha, B, m, N, slot, n, beta);
-  else    anderson_mix_kernel<1><<<grid, threads, 0, st>>>(X, F, alpha, B, m, N, slot, n, beta);
+  if (v4) DEQSCI_CUDA(launch_pdl(anderson_mix_kernel<4>, grid, threads, 0, st, X, F, alpha, B, m, N, slot, n, beta));
+  else    DEQSCI_CUDA(launch_pdl(anderson_mix_kernel<1>, grid, threads, 0, st, X, F, alpha, B, m, N, slot, n, beta));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }

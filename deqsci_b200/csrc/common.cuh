@@ -64,12 +64,12 @@ int env_int(const char* name, int dflt);
 // still draining.  Only for kernels that execute `griddepcontrol.wait` before touching anything the
 // predecessor wrote.  DEQSCI_TC_PDL=0 falls back to plain stream order.
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
   static const int pdl = env_int("DEQSCI_TC_PDL", 1);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

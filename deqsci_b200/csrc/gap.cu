@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__
                                                        float* __restrict__ zprime_out, __half* __restrict__ planes,
                                                        long long plane_elems, float sigma, int B, int H, int W,
                                                        int T, int do_gap) {
+  pdl_launch_dependents();       // launched with programmatic stream serialization: see launch_pdl (common.cuh)
+  pdl_wait_predecessor();
   constexpr int SC = (KIND == DEQSCI_NET_FFDNET) ? 2 : 1;
   constexpr int NSUB = SC * SC;
   const int Hc = H / SC, Wc = W / SC;
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(128) gap_prep_t8_kernel(const float* __restric
                                                           float* __restrict__ zprime_out, __half* __restrict__ planes,
                                                           long long plane_elems, float sigma, int B, int H, int W,
                                                           int do_gap) {
+  pdl_launch_dependents();
+  pdl_wait_predecessor();
   constexpr int SC = (KIND == DEQSCI_NET_FFDNET) ? 2 : 1;
   constexpr int NSUB = SC * SC;
   constexpr int T = 8;
@@ -335,20 +339,20 @@ int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, 
   auto a16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (T == 8 && a16(z) && a16(phi) && a16(zprime_out)) {
     if (kind == DEQSCI_NET_FFDNET)
-      gap_prep_t8_kernel<DEQSCI_NET_FFDNET><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
-                                                                               plane_elems, sigma, B, H, W, do_gap);
+      DEQSCI_CUDA(launch_pdl(gap_prep_t8_kernel<DEQSCI_NET_FFDNET>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum,
+                             zprime_out, planes, plane_elems, sigma, B, H, W, (int)do_gap));
     else
-      gap_prep_t8_kernel<DEQSCI_NET_DNCNN><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
-                                                                              plane_elems, sigma, B, H, W, do_gap);
+      DEQSCI_CUDA(launch_pdl(gap_prep_t8_kernel<DEQSCI_NET_DNCNN>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum,
+                             zprime_out, planes, plane_elems, sigma, B, H, W, (int)do_gap));
     DEQSCI_LAUNCH_CHECK();
     return DEQSCI_OK;
   }
   if (kind == DEQSCI_NET_FFDNET)
-    gap_prep_kernel<DEQSCI_NET_FFDNET><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
-                                                                          plane_elems, sigma, B, H, W, T, do_gap);
+    DEQSCI_CUDA(launch_pdl(gap_prep_kernel<DEQSCI_NET_FFDNET>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum, zprime_out,
+                           planes, plane_elems, sigma, B, H, W, T, (int)do_gap));
   else
-    gap_prep_kernel<DEQSCI_NET_DNCNN><<<(unsigned)blocks, 128, 0, st>>>(z, y, phi, phi_sum, zprime_out, planes,
-                                                                         plane_elems, sigma, B, H, W, T, do_gap);
+    DEQSCI_CUDA(launch_pdl(gap_prep_kernel<DEQSCI_NET_DNCNN>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum, zprime_out,
+                           planes, plane_elems, sigma, B, H, W, T, (int)do_gap));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }
