@@ -437,11 +437,11 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tc2::kTileM - 1) / tc2::kTileM;
   const int pairs_hw = num_sms() / 2;
-  // strip height: the largest power of two <= 16 dividing Hc that still leaves >= `rounds` strips per SM.
-  // Longer strips amortise the pipeline refill at strip boundaries (the 4-slot ring cannot prefetch the
-  // next strip's three start rows while the last tile still holds three slots)
-  static const int rounds = env_int("DEQSCI_TC_ROUNDS", 6);
-  const int R = pick_strip_rows(NF, p.tiles_x, Hc, true, 2LL * rounds * pairs_hw, 1);
+  // strip height from the cost model in tma_host.cu; DEQSCI_TC_ROUNDS=n > 0 selects the older rule instead
+  // (largest power of two <= 16 dividing Hc that leaves >= n strips per SM)
+  static const int rounds = env_int("DEQSCI_TC_ROUNDS", 0);
+  const int R = rounds > 0 ? pick_strip_rows(NF, p.tiles_x, Hc, true, 2LL * rounds * pairs_hw, 1)
+                           : pick_strip_rows_balanced(NF, p.tiles_x, Hc, true, pairs_hw, 2);
   p.strip_rows = R;
   p.strips_y = Hc / R;
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;
