@@ -86,7 +86,8 @@ __device__ __forceinline__ void pdl_wait_predecessor() { asm volatile("griddepco
 int make_plane_map(::CUtensorMap_st* map, const __half* plane, int channels, int NF, int Hc, int Wc, int box_c,
                    int box_w, int box_h, int swizzle_bytes);
 int pick_strip_rows(int NF, int tiles_x, int Hc, bool must_divide, long long min_items, int floor_rows);
-int pick_strip_rows_balanced(int NF, int tiles_x, int Hc, bool must_divide, int workers, int strips_per_item);
+int pick_strip_rows_balanced(int NF, int tiles_x, int Hc, bool must_divide, int workers, int strips_per_item,
+                             int overhead_half_rows, int min_rows);
 int env_int(const char* name, int dflt);
 
 // Activation storage between conv layers: channels-last [frames, H, W, 64], each value stored as

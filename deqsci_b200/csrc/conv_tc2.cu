@@ -441,7 +441,7 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   // (largest power of two <= 16 dividing Hc that leaves >= n strips per SM)
   static const int rounds = env_int("DEQSCI_TC_ROUNDS", 0);
   const int R = rounds > 0 ? pick_strip_rows(NF, p.tiles_x, Hc, true, 2LL * rounds * pairs_hw, 1)
-                           : pick_strip_rows_balanced(NF, p.tiles_x, Hc, true, pairs_hw, 2);
+                           : pick_strip_rows_balanced(NF, p.tiles_x, Hc, true, pairs_hw, 2, 1, 1);
   p.strip_rows = R;
   p.strips_y = Hc / R;
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;

@@ -276,7 +276,7 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcf::kTileM - 1) / tcf::kTileM;
-  const int R = pick_strip_rows(NF, p.tiles_x, Hc, false, 6LL * num_sms(), 2);
+  const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, num_sms(), 1, 1, 2);
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;

@@ -57,17 +57,20 @@ int pick_strip_rows(int NF, int tiles_x, int Hc, bool must_divide, long long min
 // Strip height by a cost model instead of a floor on the item count: a persistent worker runs
 // ceil(items / workers) strips back to back and each strip costs its R rows plus about half a row of
 // pipeline refill (3 start rows cannot be prefetched behind the previous strip), so minimise
-// rounds * (R + 0.5); ties go to the taller strip (fewer halo reloads).  items_per_worker_item = strips one
-// work item covers (2 for the CTA-pair kernel).  Fitted on batch 1..8 measurements (DESIGN.md finding 11).
-int pick_strip_rows_balanced(int NF, int tiles_x, int Hc, bool must_divide, int workers, int strips_per_item) {
-  int best = 1;
+// rounds * (R + overhead); ties go to the taller strip (fewer halo reloads).  strips_per_item = strips one
+// work item covers (2 for the CTA-pair kernel); overhead_half_rows = per-strip overhead in half rows (1 for
+// the refill above; 4 for the ky-transposed last layer, which also pushes the 2 halo rows through the MMA).
+// Fitted on batch 1..8 measurements (DESIGN.md finding 11).
+int pick_strip_rows_balanced(int NF, int tiles_x, int Hc, bool must_divide, int workers, int strips_per_item,
+                             int overhead_half_rows, int min_rows) {
+  int best = min_rows;
   long long best_cost = -1;
-  for (int R = 16; R >= 1; R /= 2) {
+  for (int R = 16; R >= min_rows; R /= 2) {
     if (must_divide && Hc % R != 0) continue;
     const long long strips = (long long)NF * tiles_x * ((Hc + R - 1) / R);
     const long long items = (strips + strips_per_item - 1) / strips_per_item;
     const long long rounds = (items + workers - 1) / workers;
-    const long long cost = rounds * (2 * R + 1);
+    const long long cost = rounds * (2 * R + overhead_half_rows);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = R; }
   }
   return best;
