@@ -115,6 +115,7 @@ struct Params {
   long long n_strips;         // real strips; strip ids >= n_strips are padding (computed on a clamped strip, not stored)
   long long n_pair_items;
   double* stats;              // STATS kernels: [gridDim.x][128] per-CTA partials: channel sums, then sums of squares
+  uint32_t lo_mask;           // experiment switch (DEQSCI_TC_LO_MASK): AND mask on each packed pair of lo' halves
   int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
   __half* dbg_out_hi;
   __half* dbg_out_lo;
@@ -314,7 +315,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
             split_f16(v[0], h0, l0);
             split_f16(v[1], h1, l1);
             hi_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            lo_pk[part * 8 + (i >> 1)] = ((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16)) & p.lo_mask;
           }
         }
         // accumulator drained: hand the TMEM buffer back to the leader's MMA thread
@@ -420,7 +421,12 @@ static void tc2_layout(Emit emit) {
       }
     }
 }
-void tc2_pack_weights(const float* w, uint8_t* img) { tc2_layout(PackWrite{w, img}); }
+void tc2_pack_weights(const float* w, uint8_t* img) {
+  tc2_layout(PackWrite{w, img});
+  const uint16_t mask = (uint16_t)env_int("DEQSCI_TC_LO_MASK", 0xFFFF);      // experiment switch, see Params::lo_mask
+  if (mask != 0xFFFF)
+    tc2_layout([&](size_t byte, int, bool lo) { if (lo) *reinterpret_cast<uint16_t*>(img + byte) &= mask; });
+}
 void tc2_pack_map(int32_t* map) { tc2_layout(PackMap{map}); }
 
 // true when the pair kernel can run this shape: full 128-pixel row tiles and a strip height that divides Hc
@@ -448,6 +454,8 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   p.n_pair_items = (p.n_strips + 1) / 2;
   static const int skip_store = env_int("DEQSCI_TC_DEBUG_SKIP_STORE", 0);
   p.debug_skip_store = skip_store;
+  static const uint32_t lo_mask16 = (uint32_t)env_int("DEQSCI_TC_LO_MASK", 0xFFFF) & 0xFFFFu;
+  p.lo_mask = lo_mask16 | (lo_mask16 << 16);
   p.stats = stats;
   p.dbg_out_hi = act_out;
   p.dbg_out_lo = act_out + plane_elems;

@@ -47,6 +47,15 @@ def make_conv(mode):
         al, wl = q((x - ah) * S, torch.float16), q((w - wh) * S, torch.float16)
         if mode == "split":
             return (conv(ah, wh) + (conv(ah, wl) + conv(al, wh)) / S).numpy()
+        if mode.startswith("split_lo"):   # lo' halves keep only the top n explicit mantissa bits (split_lo5 = 5 bits)
+            keep = int(mode[len("split_lo"):])
+            mask = torch.tensor((0xFFFF << (10 - keep)) & 0xFFFF, dtype=torch.int32)
+
+            def trunc(t):
+                b = t.to(torch.float16).view(torch.int16).to(torch.int32) & 0xFFFF
+                return (b & mask).to(torch.int16).view(torch.float16).to(torch.float32)
+            al_t, wl_t = trunc(al), trunc(wl)
+            return (conv(ah, wh) + (conv(ah, wl_t) + conv(al_t, wh)) / S).numpy()
         if mode == "acts_only":          # Ah*Wh + Al*Wh
             return (conv(ah, wh) + conv(al, wh) / S).numpy()
         a_dt = torch.float8_e5m2 if "a52" in mode else torch.float8_e4m3fn
