@@ -15,7 +15,8 @@ _ALIASES = [
     "utils", "utils.cg_utils", "operators", "operators.operator", "networks", "networks.ffdnet",
     "networks.ffdnet.models", "networks.ffdnet.functions", "networks.provable", "networks.provable.model",
     "networks.provable.model.SimpleCNN_models", "networks.provable.model.conv_sn_chen",
-    "networks.provable.model.models", "solvers",
+    "networks.provable.model.models", "networks.provable.model.realSN_models",
+    "networks.provable.model.Spectral_Normalize_chen", "solvers",
     "solvers.equilibrium_solvers_yaping", "solvers.new_equilibrium_utils_yaping",
     "training", "training.sci_equilibrium_training", "utils.sci_dataloader", "utils.metrics",
 ]

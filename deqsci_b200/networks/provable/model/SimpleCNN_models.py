@@ -12,7 +12,8 @@ from .conv_sn_chen import conv_spectral_norm
 
 
 class DnCNN(nn.Module, NativePlanCache):
-    def __init__(self, channels, num_of_layers=17, lip=1.0, no_bn=False, adaptive=False, tag='denoiser'):
+    def __init__(self, channels, num_of_layers=17, lip=1.0, no_bn=False, adaptive=False, tag='denoiser',
+                 _conv_layer=None):
         super().__init__()
         self.tag = tag
         self.channels = channels
@@ -26,6 +27,8 @@ class DnCNN(nn.Module, NativePlanCache):
             assert len(sigmas) == num_of_layers, "Length of SN list uncompatible with num of layers."
 
         def conv_layer(cin, cout, sigma):
+            if _conv_layer is not None:          # subclasses with their own conv flavour (realSN_models)
+                return _conv_layer(cin, cout)
             conv = nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
             return conv_spectral_norm(conv, sigma=sigma) if sigma > 0.0 else conv
 

@@ -5,8 +5,8 @@ string-truthy --inference and the untyped --and_maxiters), running the B200 path
         --loadpath ./models/ffdnet.ckpt --denoiser ffdnet --and_maxiters 180 --inference True
 
 Denoisers on the path built here: ffdnet, SimpleCNN, RealSN_SimpleCNN (the three shipped
-checkpoints) and DnCNN (the 17-layer BatchNorm DnCNN, same conv stack).  The U-Net / ResNet / 17-layer choices of the reference are outside the DE-GAP scope
- and raise NotImplementedError."""
+checkpoints), DnCNN and RealSN_DnCNN (the 17-layer BatchNorm DnCNNs, same conv stack).  The U-Net / ResNet
+choices of the reference are outside the DE-GAP scope and raise NotImplementedError."""
 import argparse
 import os
 
@@ -50,6 +50,9 @@ def build_denoiser(name):
         return DnCNN(1, num_of_layers=4, lip=1.0, no_bn=True, tag='denoiser')
     if name == 'DnCNN':
         from .networks.provable.model.models import DnCNN
+        return DnCNN(channels=1, num_of_layers=17, tag='denoiser')
+    if name == 'RealSN_DnCNN':
+        from .networks.provable.model.realSN_models import DnCNN
         return DnCNN(channels=1, num_of_layers=17, tag='denoiser')
     raise NotImplementedError('unknown denoiser! (%r is not on the DE-GAP path of this build)' % name)
 

@@ -201,6 +201,51 @@ def stage_dncnn_bn():
     print("dncnn_bn", y.shape, float(y.abs().max()))
 
 
+def realsn_probe(shape, layer):
+    """Deterministic stand-in for the random power-iteration probe `weight_u` (so the fixture need not store
+    400 KB of noise per layer): unit-norm sin pattern; tests/test_gpu_parity.py rebuilds it the same way."""
+    n = int(np.prod(shape))
+    u = torch.sin(torch.arange(n, dtype=torch.float32) * 0.37 + 1.3 * layer).reshape(shape)
+    return u / float(torch.sqrt(torch.sum(u * u)))
+
+
+def stage_realsn_dncnn():
+    """realSN_models.DnCNN (`--denoiser RealSN_DnCNN`) with 3 layers, seeded random weights: (a) one
+    TRAIN-mode forward on a [2,1,40,72] input -- the spectral-norm hook runs one power iteration per conv
+    and stores `weight` / `weight_u` -- with the state before and after (probes `weight_u`: generated by
+    realsn_probe before, every 16th element stored after); (b) the EVAL-mode output on the same input with
+    the stored weights."""
+    ref_import.install_shims()
+    from networks.provable.model.realSN_models import DnCNN
+    torch.manual_seed(11)
+    net = DnCNN(channels=1, num_of_layers=3, tag='denoiser')
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    for i, m in enumerate(net.dncnn):
+        if hasattr(m, "weight_u"):
+            m.weight_u.copy_(realsn_probe(tuple(m.weight_u.shape), i))
+    out = {}
+    for k, v in net.state_dict().items():
+        if not k.endswith("weight_u"):
+            out["sd0::" + k] = v.clone().numpy()
+    x = torch.rand(2, 1, 40, 72)
+    net.train()
+    y_train = net(x)
+    for k, v in net.state_dict().items():
+        v = v.detach().clone().numpy()
+        out["sd1::" + k] = v.reshape(-1)[::16].copy() if k.endswith("weight_u") else v
+    net.eval()
+    with torch.no_grad():
+        y_eval = net(x)
+    out.update(x=x.numpy(), y_train=y_train.detach().numpy(), y_eval=y_eval.numpy())
+    np.savez_compressed(os.path.join(HERE, "realsn_dncnn_vectors.npz"), **out)
+    print("realsn_dncnn", y_eval.shape, float(y_eval.abs().max()), float(y_train.detach().abs().max()))
+
+
 def stage_train(wide=False):
     """One implicit-differentiation training step (reference training/sci_equilibrium_training.py:54-75)
     on a 32x32x8 crop (wide: 32x160x8, large enough for the native train-mode kernels), B=2,
@@ -246,7 +291,7 @@ def stage_train(wide=False):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "train_wide", "dncnn_bn"])
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "train_wide", "dncnn_bn", "realsn_dncnn"])
     ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
     ap.add_argument("--scenes", nargs="*", default=SCENES)
     a = ap.parse_args()
@@ -261,5 +306,7 @@ if __name__ == "__main__":
         stage_train(wide=True)
     elif a.stage == "dncnn_bn":
         stage_dncnn_bn()
+    elif a.stage == "realsn_dncnn":
+        stage_realsn_dncnn()
     else:
         stage_full(a.denoisers, a.scenes)

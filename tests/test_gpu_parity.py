@@ -535,6 +535,19 @@ def test_dncnn_batchnorm_variant(dev):
     assert rel_l2(got, want) <= 5e-5
 
 
+def test_realsn_dncnn_eval_native(dev):
+    """`--denoiser RealSN_DnCNN`: eval mode uses the stored `weight` buffers (reference
+    Spectral_Normalize_chen.py:87-89) with BatchNorm folded, on the native conv stack; against the reference's
+    own eval output after its train-mode step (so the buffers are the normalised weights)."""
+    from test_host_cpu import _realsn_fixture
+    net, v = _realsn_fixture()
+    sd1 = {k[len("sd1::"):]: torch.from_numpy(v[k]) for k in v if k.startswith("sd1::") and not k.endswith("weight_u")}
+    net.load_state_dict(sd1, strict=False)       # probes are not needed in eval mode
+    net = net.eval().to(dev)
+    got = net(t(v["x"], dev)).cpu().numpy()
+    assert rel_l2(got, v["y_eval"]) <= 2e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # (8) the boundary really is a C-ABI: a plain-C host program against include/deqsci.h
 # ---------------------------------------------------------------------------------------------

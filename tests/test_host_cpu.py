@@ -149,3 +149,42 @@ def test_c_abi_argument_validation_without_gpu():
     assert L.deqsci_denoiser_workspace_bytes(None, 1, 8, 8, 8) == 0
     assert L.deqsci_reconstruct_workspace_bytes(None, 1, 8, 8, 8, 5) == 0
     assert L.deqsci_denoiser_destroy(None) == 0
+
+
+def _realsn_fixture():
+    from conftest import GOLDEN
+    v = dict(np.load(os.path.join(GOLDEN, "realsn_dncnn_vectors.npz")))
+    from deqsci_b200.networks.provable.model.realSN_models import DnCNN as RealSNDnCNN
+    net = RealSNDnCNN(channels=1, num_of_layers=3)
+    sd = {k[len("sd0::"):]: torch.from_numpy(v[k]) for k in v if k.startswith("sd0::")}
+    for i, m in enumerate(net.dncnn):            # the probes: same deterministic pattern as the generator
+        if hasattr(m, "weight_u"):
+            n = m.weight_u.numel()
+            u = torch.sin(torch.arange(n, dtype=torch.float32) * 0.37 + 1.3 * i).reshape(m.weight_u.shape)
+            sd["dncnn.%d.weight_u" % i] = u / float(torch.sqrt(torch.sum(u * u)))
+    net.load_state_dict(sd, strict=True)         # same keys as the reference's realSN_models.DnCNN
+    return net, v
+
+
+def test_realsn_dncnn_train_mode_matches_reference():
+    """`--denoiser RealSN_DnCNN` (reference networks/provable/model/realSN_models.py + Spectral_Normalize_chen.py):
+    one train-mode forward = one power iteration per conv (full-correlation adjoint, 0.3**(1/17) factor),
+    batch-statistics BatchNorm; output, normalised weights, probes and running statistics against the
+    reference's own run (tests/golden/make_golden.py --stage realsn_dncnn).  Train mode is PyTorch on either
+    device; the eval-mode native path is checked in tests/test_gpu_parity.py."""
+    net, v = _realsn_fixture()
+    net.train()
+    y = net(torch.from_numpy(v["x"]))
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    assert rel(y.detach().numpy(), v["y_train"]) <= 1e-5
+    after = net.state_dict()
+    for k in v:
+        if not k.startswith("sd1::"):
+            continue
+        got = after[k[len("sd1::"):]].detach().numpy()
+        if k.endswith("weight_u"):
+            got = got.reshape(-1)[::16]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(v[k])
+        else:
+            assert rel(got.astype(np.float64), v[k].astype(np.float64)) <= 1e-5, k
