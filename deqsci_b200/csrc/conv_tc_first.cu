@@ -23,7 +23,7 @@ using namespace ptx;
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 320;
-constexpr int kSlots = 6;
+constexpr int kSlots = 4;
 constexpr int kRowBytes = 32;                                  // 16 channels fp16
 constexpr int kPlaneBytes = 5 * 1024;                          // 130 pixels x 32 B = 4160 B, padded
 constexpr int kSlotBytes = 2 * kPlaneBytes;
@@ -58,7 +58,7 @@ __device__ __forceinline__ Item decode(const Params& p, long long item) {
   return it;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
                      const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
                      const Params p) {
@@ -276,7 +276,7 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcf::kTileM - 1) / tcf::kTileM;
-  const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, num_sms(), 1, 1, 2);
+  const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, 2 * num_sms(), 1, 1, 2);
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
@@ -286,7 +286,7 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
   if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
-  const int grid = (int)(p.n_items < num_sms() ? p.n_items : num_sms());
+  const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM
   DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    tcf::kSmemBytes));
   ProfScope prof(PK_CONV_FIRST, st);

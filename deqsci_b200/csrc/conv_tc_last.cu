@@ -34,9 +34,9 @@ constexpr int kSlotBytes = 2 * kPlaneBytes;
 constexpr int kTxBytes = 2 * (kTileM + 2) * 128;
 constexpr int kKxBytesB = 32 * 128;                 // per kx: [16 hi rows | 16 lo' rows] x 64 k
 constexpr int kWBytes = 3 * kKxBytesB;              // 12 KB
-constexpr int kBufs = 4;                            // accumulator ring (input rows in flight)
+constexpr int kBufs = 8;                            // accumulator ring capacity (input rows in flight: Params::bufs <= kBufs)
 constexpr int kBufCols = 32;
-constexpr int kTmemCols = kBufs * kBufCols;         // 128
+constexpr int kTmemCols = kBufs * kBufCols;         // 256
 constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 1024;
 
 struct Params {
@@ -50,6 +50,7 @@ struct Params {
   const float* zprime;
   float* out_cube;
   int H, W, T;
+  int bufs;                   // accumulator buffers in use (4..kBufs)
 };
 struct Item { int nf, h0, w0, ntiles; };
 
@@ -139,12 +140,13 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
       const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
       int slot = 0;
       uint32_t phase = 0;
+      const uint32_t nb = (uint32_t)p.bufs;
       uint32_t g = 0;                                            // running input-row counter -> buffer ring
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const Item it = decode(p, item);
         for (int q = 0; q < it.ntiles + 2; ++q, ++g) {
-          const int buf = g % kBufs;
-          mbar_wait(bar_tempty(buf), ((g / kBufs) & 1) ^ 1);
+          const int buf = g % nb;
+          mbar_wait(bar_tempty(buf), ((g / nb) & 1) ^ 1);
           mbar_wait(bar_full(slot), phase);
           tc_fence_after();
           const uint32_t d = tmem_base + buf * kBufCols;
@@ -172,6 +174,7 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t nb = (uint32_t)p.bufs;
     uint32_t g0 = 0;                                             // counter of the strip's first input row
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode(p, item);
@@ -191,14 +194,14 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
         }
         while (rows_ready < j + 3) {
           const uint32_t g = g0 + rows_ready;
-          mbar_wait(bar_tfull(g % kBufs), (g / kBufs) & 1);
+          mbar_wait(bar_tfull(g % nb), (g / nb) & 1);
           ++rows_ready;
         }
         tc_fence_after();
         uint32_t acc[3][4], cor[3][4];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const uint32_t t_addr = lane_base + ((g0 + j + ky) % kBufs) * kBufCols;
+          const uint32_t t_addr = lane_base + ((g0 + j + ky) % nb) * kBufCols;
           const int col = (COUT == 4) ? 4 * ky : 0;              // COUT == 1: columns 0,1,2 sit in one x4 load
           tmem_ld4(t_addr + col, acc[ky]);
           tmem_ld4(t_addr + 16 + col, cor[ky]);
@@ -207,10 +210,10 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_tempty((g0 + j) % kBufs));              // V_j is dead after output row j
+          mbar_arrive(bar_tempty((g0 + j) % nb));              // V_j is dead after output row j
           if (j == it.ntiles - 1) {                               // end of strip: its last two rows too
-            mbar_arrive(bar_tempty((g0 + j + 1) % kBufs));
-            mbar_arrive(bar_tempty((g0 + j + 2) % kBufs));
+            mbar_arrive(bar_tempty((g0 + j + 1) % nb));
+            mbar_arrive(bar_tempty((g0 + j + 2) % nb));
           }
         }
         if (w < p.Wc) {
@@ -279,6 +282,8 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
   p.zprime = zprime; p.out_cube = out_cube; p.H = H; p.W = W; p.T = T;
+  static const int bufs = env_int("DEQSCI_TCL_BUFS", tcl::kBufs);
+  p.bufs = bufs < 4 ? 4 : (bufs > tcl::kBufs ? tcl::kBufs : bufs);
   CUtensorMap in_hi, in_lo;
   int rc;
   if ((rc = make_plane_map(&in_hi, act_in, 64, NF, Hc, Wc, 64, tcl::kTileM + 2, 1, 128))) return rc;

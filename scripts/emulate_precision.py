@@ -56,6 +56,8 @@ def make_conv(mode):
                 return (b & mask).to(torch.int16).view(torch.float16).to(torch.float32)
             al_t, wl_t = trunc(al), trunc(wl)
             return (conv(ah, wh) + (conv(ah, wl_t) + conv(al_t, wh)) / S).numpy()
+        if mode == "weights_only":       # Ah*Wh + Ah*Wl: activations rounded to fp16, weights carried in full
+            return (conv(ah, wh) + conv(ah, wl) / S).numpy()
         if mode == "acts_only":          # Ah*Wh + Al*Wh
             return (conv(ah, wh) + conv(al, wh) / S).numpy()
         a_dt = torch.float8_e5m2 if "a52" in mode else torch.float8_e4m3fn
