@@ -8,3 +8,7 @@ for tool in memcheck racecheck; do
 done
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_memcheck_smoke.log 2>&1; echo "memcheck smoke exit $?"
 grep -E "ERROR SUMMARY|smoke ok" gpurun_out/sanitizer_memcheck_smoke.log | tail -3
+# the tensor-core kernels on wide images (CTA-pair hidden layers, first / last layers, PDL chain) and the
+# train-mode statistics epilogue
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests -q -m gpu -x -k "wide_images or train_mode_batchnorm or plan_refresh" > gpurun_out/sanitizer_memcheck_tc.log 2>&1; echo "memcheck tensor-core kernels exit $?"
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_memcheck_tc.log | tail -3
