@@ -13,6 +13,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_parti
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, double count) {
+  pdl_launch_dependents();       // launched with programmatic stream serialization: see launch_pdl (common.cuh)
+  pdl_wait_predecessor();
   // 1024 threads: 8 row groups x 128 columns of the per-CTA partials; every column is added up in a fixed
   // order (group-strided rows, then the 8 groups), so the statistics are deterministic
   __shared__ double part[8][2 * kHidden];
@@ -48,6 +50,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_parti
 __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act, long long plane_elems,
                                                        const float* __restrict__ scale_shift, int relu) {
   __shared__ float ss[2 * kHidden];
+  pdl_launch_dependents();
+  pdl_wait_predecessor();
   if (threadIdx.x < 2 * kHidden) ss[threadIdx.x] = scale_shift[threadIdx.x];
   __syncthreads();
   const long long n_vec = plane_elems / 8;     // 8 channels (16 bytes per plane) per step
@@ -74,15 +78,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act,
 int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     long long count, int relu, cudaStream_t st) {
-  bn_finalize_kernel<<<1, 8 * 2 * kHidden, 0, st>>>(stats, n_partials, scale_shift, gamma, beta, running_mean, running_var,
-                                                momentum, eps, (double)count);
-  DEQSCI_LAUNCH_CHECK();
+  DEQSCI_CUDA(launch_pdl(bn_finalize_kernel, 1, 8 * 2 * kHidden, 0, st, stats, n_partials, scale_shift, gamma, beta,
+                         running_mean, running_var, momentum, eps, (double)count));
   long long blocks = (plane_elems / 8 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   ProfScope prof(PK_GAP, st);
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(act, plane_elems, scale_shift, relu);
-  DEQSCI_LAUNCH_CHECK();
+  DEQSCI_CUDA(launch_pdl(bn_apply_kernel, (unsigned)blocks, 256, 0, st, act, plane_elems, (const float*)scale_shift, relu));
   return DEQSCI_OK;
 }
 
