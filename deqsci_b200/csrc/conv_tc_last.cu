@@ -28,7 +28,7 @@ using namespace ptx;
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 192;
-constexpr int kSlots = 6;
+constexpr int kSlots = 2;
 constexpr int kPlaneBytes = 17 * 1024;              // 130 pixels x 128 B, padded to the 1 KB swizzle atom
 constexpr int kSlotBytes = 2 * kPlaneBytes;
 constexpr int kTxBytes = 2 * (kTileM + 2) * 128;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 }
 
 template <int COUT>   // 4: FFDNet (pixel shuffle), 1: DnCNN
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
                     const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -277,7 +277,7 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcl::kTileM - 1) / tcl::kTileM;
-  const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, num_sms(), 1, 4, 2);
+  const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, 2 * num_sms(), 1, 4, 2);
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
@@ -288,7 +288,7 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   int rc;
   if ((rc = make_plane_map(&in_hi, act_in, 64, NF, Hc, Wc, 64, tcl::kTileM + 2, 1, 128))) return rc;
   if ((rc = make_plane_map(&in_lo, act_in + plane_elems, 64, NF, Hc, Wc, 64, tcl::kTileM + 2, 1, 128))) return rc;
-  const int grid = (int)(p.n_items < num_sms() ? p.n_items : num_sms());
+  const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM
   ProfScope prof(PK_CONV_LAST, st);
   if (cout == 4) {
     DEQSCI_CUDA(cudaFuncSetAttribute(tcl::conv_last_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
