@@ -7,7 +7,8 @@
 // UMMA descriptor 32 bytes (one pixel) further into a TMA-loaded input row (32-byte swizzle).
 //
 // Structure = the rolling-row pipeline of conv_tc.cu (LD_ROLL) with the epilogue of conv_tc2.cu:
-// warp 0 TMA producer (6-slot ring of input rows with 1-pixel halo, hi + lo planes), warp 1 TMEM
+// two CTAs per SM (110 KB, 96 registers, 256 TMEM columns each) hide each other's epilogue latency;
+// warp 0 TMA producer (4-slot ring of input rows with 1-pixel halo, hi + lo planes), warp 1 TMEM
 // allocator + MMA issuer, warps 2-9 epilogue (tcgen05.ld -> affine + ReLU -> hi/lo split -> swizzled
 // smem -> TMA store of 32 pixels x 32 channels per warp and plane).
 #include <cuda.h>

@@ -12,8 +12,9 @@
 // while it applies the affine, the pixel shuffle (networks/ffdnet/functions.py:63-81) and
 // z' - noise (solvers/equilibrium_solvers_yaping.py:417,420).  24 MMAs per row instead of 72.
 //
-// Warp roles (192 threads): warp 0 TMA producer (6-slot streaming ring of input rows, hi + lo planes,
-// every row used once), warp 1 TMEM allocator + MMA issuer (ring of 4 accumulator buffers x 32
+// Two CTAs per SM (82 KB of shared memory, 256 TMEM columns each) hide each other's pipeline latencies.
+// Warp roles (192 threads): warp 0 TMA producer (2-slot streaming ring of input rows, hi + lo planes,
+// every row used once), warp 1 TMEM allocator + MMA issuer (ring of 8 accumulator buffers x 32
 // columns: [16 main | 16 corr]), warps 2-5 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
