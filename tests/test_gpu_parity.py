@@ -549,6 +549,45 @@ def test_realsn_dncnn_eval_native(dev):
 
 
 # ---------------------------------------------------------------------------------------------
+# (7b) full-size properties (256x256x8, the north-star shape): what must hold at any size
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", ["ffdnet", "SimpleCNN"])
+def test_full_size_properties(dev, d):
+    """At BASELINE.json's full size the oracle is too slow to rerun in a test, so the CUDA path is checked
+    through size-independent properties, all bit-exact:
+      * batch independence (= sharding invariance): measurement i reconstructed inside a batch of
+        three equals measurement i reconstructed alone (per-sample Anderson weights, no cross-sample term);
+      * frame equivariance of the denoiser: permuting the T frames of a cube permutes its output;
+      * data consistency of the GAP step: A(z') == y to fp32 rounding, and z' is a fixed point of the step."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_, Phi_sum_
+    from deqsci_b200 import ops
+    data = orc.synthetic_measurements(64, 3)                        # 256 x 256 x 8
+    y, Phi = t(data["y"], dev), t(data["Phi"], dev)
+    Ps = Phi_sum_(Phi)
+    solver = build_solver(d, dev)
+
+    def recon(sl):
+        deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=10, tol=1e-5)
+        return deq.forward(y[sl], Phi[sl], Ps[sl], initial_point=At_torch_(y[sl], Phi[sl]), train_flag=False)
+
+    whole = recon(slice(0, 3))
+    assert torch.isfinite(whole).all()
+    for i in range(3):
+        assert torch.equal(recon(slice(i, i + 1))[0], whole[i]), "measurement %d depends on its batch" % i
+
+    plan = solver.nonlinear_op.native_plan(dev)
+    z = At_torch_(y, Phi)
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device=dev)
+    base = plan.denoise_residual(z, 0.2)
+    assert torch.equal(plan.denoise_residual(z[..., perm].contiguous(), 0.2), base[..., perm])
+
+    zp = ops.gap_step(z, y, Phi, Ps)
+    assert rel_l2(A_torch_(zp, Phi).cpu().numpy(), data["y"]) <= 1e-6
+    assert rel_l2(ops.gap_step(zp, y, Phi, Ps).cpu().numpy(), zp.cpu().numpy()) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
 # (8) the boundary really is a C-ABI: a plain-C host program against include/deqsci.h
 # ---------------------------------------------------------------------------------------------
 def test_c_abi_from_plain_c(dev, tmp_path):
