@@ -65,6 +65,9 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, _P]),
     "deqsci_reconstruct_train": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(SolverOpts), POINTER(BNParams), c_float,
                                          c_float, _P, c_size_t, POINTER(SolverResult), c_int, c_int, c_int, c_int, _P]),
+    "deqsci_adjoint_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "deqsci_adjoint_solve": (c_int, [_P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
+                                     c_int, c_int, c_int, c_int, _P]),
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),

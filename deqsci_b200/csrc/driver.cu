@@ -27,11 +27,16 @@ Layout layout(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
   L.scratch_floats = align_up_sz(deqsci_anderson_scratch_floats(B, m, (long long)N), 64);
   L.floats_total = L.hist_floats + L.gram_floats + L.alpha_floats + L.scratch_floats + 64 /*res*/ +
                    (size_t)kMaxBnLayers * 2 * kHidden /*running-statistics snapshot*/;
-  L.den_bytes = deqsci_denoiser_workspace_bytes(h, B, H, W, T);
+  L.den_bytes = h ? deqsci_denoiser_workspace_bytes(h, B, H, W, T) : 0;
   L.total_bytes = 1024 + align_up_sz(L.floats_total * sizeof(float), 1024) + L.den_bytes;
   return L;
 }
 }  // namespace
+
+extern "C" size_t deqsci_adjoint_solve_workspace_bytes(int B, int H, int W, int T, int m) {
+  if (B <= 0 || H <= 0 || W <= 0 || T <= 0 || m < 2 || m > 8) return 0;
+  return layout(nullptr, B, H, W, T, m).total_bytes;
+}
 
 extern "C" size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
   if (!h || B <= 0 || H <= 0 || W <= 0 || T <= 0 || m < 2 || m > 8) return 0;
@@ -40,15 +45,23 @@ extern "C" size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, i
 }
 
 namespace {
-// bn == nullptr: eval-mode plan (BatchNorm folded); else train-mode f calls (deqsci_iterate_train)
+// The andersonexp loop on one of three maps:
+//   h, bn == nullptr : f = the iterate map, eval-mode plan (BatchNorm folded)
+//   h, bn            : f = the iterate map in train mode (deqsci_iterate_train)
+//   h == nullptr     : f(v) = gap_vjp(v) + adjoint_grad, the backward fixed-point map of tag 'ffdnet'
+//                      (solvers/new_equilibrium_utils_yaping.py:274-277); y is unused
 int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
                      const float* x0, float* out, const deqsci_solver_opts* o, const deqsci_bn_params* bn,
-                     float momentum, float eps, void* workspace, size_t workspace_bytes,
-                     deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
-  DEQSCI_CHECK_ARG(h && y && phi && phi_sum && out && o && workspace && result, "reconstruct: null pointer");
+                     float momentum, float eps, const float* adjoint_grad, void* workspace,
+                     size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
+                     void* stream) {
+  DEQSCI_CHECK_ARG((h || adjoint_grad) && (y || adjoint_grad) && phi && phi_sum && out && o && workspace && result,
+                   "reconstruct: null pointer");
   DEQSCI_CHECK_ARG(o->m >= 2 && o->m <= 8, "reconstruct: m=%d unsupported (2..8)", o->m);
   DEQSCI_CHECK_ARG(o->max_iter >= 2, "reconstruct: max_iter=%d (need >= 2)", o->max_iter);
-  const size_t need = deqsci_reconstruct_workspace_bytes(h, B, H, W, T, o->m);
+  DEQSCI_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0, "reconstruct: non-positive dimension");
+  const size_t need = h ? deqsci_reconstruct_workspace_bytes(h, B, H, W, T, o->m)
+                        : deqsci_adjoint_solve_workspace_bytes(B, H, W, T, o->m);
   DEQSCI_CHECK_ARG(need != 0, "reconstruct: unsupported shape B=%d H=%d W=%d T=%d", B, H, W, T);
   if (workspace_bytes < need) {
     set_error("reconstruct: workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
@@ -82,6 +95,7 @@ int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi,
     sigma_prev = sigma;
     sigma = sigma * o->sigma_decay;
     ++calls;
+    if (!h) return deqsci_gap_vjp(zin, phi, phi_sum, adjoint_grad, zout, B, H, W, T, stream);
     if (bn)
       return deqsci_iterate_train(h, zin, y, phi, phi_sum, sigma_prev, zout, den_ws, L.den_bytes, bn, momentum, eps, B,
                                   H, W, T, stream);
@@ -92,6 +106,7 @@ int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi,
   int rc;
   DEQSCI_CUDA(cudaMemsetAsync(gram, 0, (L.gram_floats + L.alpha_floats) * sizeof(float), st));
   if (x0) DEQSCI_CUDA(cudaMemcpyAsync(Xs(0), x0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else if (!h) DEQSCI_CUDA(cudaMemcpyAsync(Xs(0), adjoint_grad, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
   else if ((rc = deqsci_gap_adjoint(y, phi, Xs(0), B, H, W, T, stream))) return rc;      // initial_point = At(y)
   if ((rc = f_call(Xs(0), Fs(0)))) return rc;
   DEQSCI_CUDA(cudaMemcpyAsync(Xs(1), Fs(0), slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -159,8 +174,9 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
                                   const float* x0, float* out, const deqsci_solver_opts* o, void* workspace,
                                   size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
                                   void* stream) {
-  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, nullptr, 0.f, 0.f, workspace, workspace_bytes, result, B, H,
-                          W, T, stream);
+  DEQSCI_CHECK_ARG(h != nullptr, "reconstruct: null denoiser handle");
+  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, nullptr, 0.f, 0.f, nullptr, workspace, workspace_bytes, result,
+                          B, H, W, T, stream);
 }
 
 extern "C" int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y, const float* phi,
@@ -169,6 +185,17 @@ extern "C" int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y
                                         float eps, void* workspace, size_t workspace_bytes,
                                         deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
   DEQSCI_CHECK_ARG(bn != nullptr, "reconstruct_train: null BatchNorm table");
-  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, bn, momentum, eps, workspace, workspace_bytes, result, B, H,
-                          W, T, stream);
+  DEQSCI_CHECK_ARG(h != nullptr, "reconstruct_train: null denoiser handle");
+  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, bn, momentum, eps, nullptr, workspace, workspace_bytes, result,
+                          B, H, W, T, stream);
+}
+
+extern "C" int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_sum, float* out,
+                                    const deqsci_solver_opts* o, void* workspace, size_t workspace_bytes,
+                                    deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(grad != nullptr && o != nullptr, "adjoint_solve: null pointer");
+  deqsci_solver_opts opts = *o;
+  opts.final_call = 0;                 // the reference returns the solver's iterate, not one more evaluation
+  return reconstruct_impl(nullptr, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
+                          workspace_bytes, result, B, H, W, T, stream);
 }

@@ -1,6 +1,8 @@
 """Thin tensor-level wrappers over the C-ABI: shape / dtype / device checks, raw pointers, the
 current CUDA stream.  PyTorch is plumbing here (device memory + streams); all arithmetic happens
 in libdeqsci.so."""
+import ctypes
+
 import torch
 
 from . import _lib
@@ -107,3 +109,35 @@ def gap_vjp(v, phi, phi_sum_, add=None, out=None):
                                        add.data_ptr() if add is not None else None, out.data_ptr(),
                                        B, H, W, T, _stream(v)), "deqsci_gap_vjp")
     return out
+
+
+_adjoint_ws = {}
+
+
+def adjoint_solve(grad, phi, phi_sum_, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5):
+    """andersonexp on g -> gap_vjp(g) + grad, started at grad, in ONE C-ABI call (deqsci_adjoint_solve): the
+    backward solve of DEQFixedPoint's hook for tag 'ffdnet' (reference
+    solvers/new_equilibrium_utils_yaping.py:274-277).  Returns (g [B,H,W,T], backward_res)."""
+    from . import _lib
+    grad, phi, phi_sum_ = _req(grad, "grad", 4), _req(phi, "Phi", 4), _req(phi_sum_, "Phi_sum", 3)
+    phi = _bcast_phi(phi, grad)
+    phi_sum_ = _bcast_phi(phi_sum_, grad)
+    B, H, W, T = _cube_dims(grad)
+    if tuple(phi.shape) != (B, H, W, T) or tuple(phi_sum_.shape) != (B, H, W):
+        raise DeqsciError("adjoint_solve: inconsistent shapes grad %s Phi %s Phi_sum %s" % (
+            tuple(grad.shape), tuple(phi.shape), tuple(phi_sum_.shape)))
+    need = lib().deqsci_adjoint_solve_workspace_bytes(B, H, W, T, int(m))
+    if need == 0:
+        raise DeqsciError("adjoint_solve: unsupported shape or history m=%d" % m)
+    ws = _adjoint_ws.get(grad.device)
+    if ws is None or ws.numel() < need:
+        _adjoint_ws[grad.device] = None
+        ws = _adjoint_ws[grad.device] = torch.empty(need, dtype=torch.uint8, device=grad.device)
+    out = torch.empty_like(grad)
+    opts = _lib.SolverOpts(int(m), float(lam), float(beta), int(max_iter), float(tol), 0.0, 1.0, 0, 0, 1e-5)
+    res = _lib.SolverResult()
+    with torch.cuda.device(grad.device):
+        check(lib().deqsci_adjoint_solve(grad.data_ptr(), phi.data_ptr(), phi_sum_.data_ptr(), out.data_ptr(),
+                                         ctypes.byref(opts), ws.data_ptr(), ws.numel(), ctypes.byref(res), B, H, W, T,
+                                         _stream(grad)), "deqsci_adjoint_solve")
+    return out, float(res.residual)

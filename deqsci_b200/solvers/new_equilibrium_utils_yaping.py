@@ -294,6 +294,12 @@ class DEQFixedPoint(nn.Module):
             f0 = self.f(z0, x, Phi, Phi_sum)
 
         def backward_hook(grad):
+            import os
+            if (native_vjp and self.solver is andersonexp and os.environ.get("DEQSCI_DRIVER", "1") != "0"
+                    and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"}
+                    and self.kwargs.get("max_iter", 50) >= 2 and grad.dtype == torch.float32):
+                g, self.backward_res = ops.adjoint_solve(grad.contiguous(), Phi, Phi_sum, **self.kwargs)
+                return g
             if native_vjp:
                 g0 = grad.contiguous()
                 vjp = lambda v, out=None: ops.gap_vjp(v, Phi, Phi_sum, add=g0, out=out)

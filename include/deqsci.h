@@ -233,6 +233,16 @@ int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y, const flo
                              void* workspace, size_t workspace_bytes, deqsci_solver_result* result,
                              int B, int H, int W, int T, void* stream);
 
+/* The backward fixed-point solve of the implicit-differentiation hook for tag 'ffdnet'
+ * (solvers/new_equilibrium_utils_yaping.py:274-277): andersonexp on g -> VJP_f(g) + grad starting at grad,
+ * where VJP_f is the GAP projector (deqsci_gap_vjp) because FFDNet detaches its input.  out = the solver's
+ * last iterate (what the reference's hook returns as the gradient w.r.t. z); result->residual is
+ * `backward_res`.  opts: m, lam, beta, max_iter, tol, res_eps (sigma fields and final_call are ignored). */
+size_t deqsci_adjoint_solve_workspace_bytes(int B, int H, int W, int T, int m);
+int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_sum, float* out,
+                         const deqsci_solver_opts* opts, void* workspace, size_t workspace_bytes,
+                         deqsci_solver_result* result, int B, int H, int W, int T, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Launch accounting and sampled device timing of the library's own kernels.
  * Kernel classes: 0 gap, 1 conv_first, 2 conv_hidden, 3 conv_last, 4 anderson_gram,

@@ -144,7 +144,8 @@ def test_train_driver_equals_python_loop(train_wide_vectors, d, monkeypatch):
         monkeypatch.setenv("DEQSCI_DRIVER", driver)
         solver, deq, rec, loss = _step(d, train_wide_vectors, dev)
         out[driver] = (rec.detach().clone(), {k: p.grad.clone() for k, p in solver.named_parameters() if p.grad is not None},
-                       {k: b.clone() for k, b in solver.named_buffers()}, getattr(solver, "_n", None), deq.forward_res)
+                       {k: b.clone() for k, b in solver.named_buffers()}, getattr(solver, "_n", None), deq.forward_res,
+                       deq.backward_res)
     a, b = out["1"], out["0"]
     assert torch.equal(a[0], b[0])
     # gradients come out of cuDNN's backward kernels (atomics): equal up to their run-to-run noise
@@ -154,6 +155,10 @@ def test_train_driver_equals_python_loop(train_wide_vectors, d, monkeypatch):
     assert all(torch.equal(a[2][k], b[2][k]) for k in a[2])
     assert a[3] == b[3]
     assert a[4] == b[4]
+    if d == "ffdnet":                    # backward solve: deqsci_adjoint_solve vs the Python loop on the same kernels
+        assert a[5] == b[5]
+    else:
+        assert abs(a[5] - b[5]) <= 1e-4 * abs(b[5])
 
 
 @pytest.mark.parametrize("d", ["SimpleCNN", "ffdnet"])
