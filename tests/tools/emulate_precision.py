@@ -2,9 +2,10 @@
 """CPU emulation of candidate tensor-core operand formats for the 64->64 hidden convolutions: runs the
 oracle's DE-GAP solve with the hidden convs' operands quantised as a kernel would see them and reports
 the per-iterate relative L2 distance and the PSNR shift against the fp32 run.  Design-time tool only
-(decides whether a cheaper operand split can hold the parity bar); nothing in the product imports it.
+(decides whether a cheaper operand split can hold the parity bar); it lives under tests/ because it runs
+the oracle, which only test infrastructure may do.  Nothing in the product imports it.
 
-    python scripts/emulate_precision.py ffdnet kobe 128 60
+    python tests/tools/emulate_precision.py ffdnet drop8 128 40
 """
 import os
 import sys
@@ -13,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_scene, load_weights  # noqa: E402
