@@ -4,6 +4,7 @@
 // C++ loop.  No per-iteration host round trip stalls the device: every iteration's residual lands in
 // pinned host memory through a 16-byte async copy + event, and the host tests iteration k-1 while
 // iteration k is already queued (rolling back one speculative sigma step on convergence).
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -12,6 +13,56 @@ using namespace deqsci;
 
 namespace {
 size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Residual ring (pinned host floats + one event per iteration), pooled across calls: cudaMallocHost and
+// event creation cost about a millisecond per reconstruction otherwise.  A ring belongs to one call at a
+// time (concurrent calls on different threads each take their own); events belong to the device that was
+// current when they were created.
+struct ResidualRing {
+  float* host = nullptr;
+  int capacity = 0, device = -1;
+  std::vector<cudaEvent_t> events;
+};
+std::mutex g_ring_mutex;
+std::vector<ResidualRing*> g_free_rings;
+
+ResidualRing* acquire_ring(int iters) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  ResidualRing* r = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    for (size_t i = 0; i < g_free_rings.size(); ++i)
+      if (g_free_rings[i]->device == dev) {
+        r = g_free_rings[i];
+        g_free_rings.erase(g_free_rings.begin() + i);
+        break;
+      }
+  }
+  if (!r) { r = new ResidualRing(); r->device = dev; }
+  if (r->capacity < iters) {
+    if (r->host) cudaFreeHost(r->host);
+    r->host = nullptr;
+    r->capacity = 0;
+    if (cudaMallocHost(&r->host, (size_t)iters * 4 * sizeof(float)) != cudaSuccess) { delete r; return nullptr; }
+    r->capacity = iters;
+  }
+  while ((int)r->events.size() < iters) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) break;
+    r->events.push_back(e);
+  }
+  if ((int)r->events.size() < iters) {
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    g_free_rings.push_back(r);
+    return nullptr;
+  }
+  return r;
+}
+void release_ring(ResidualRing* r) {
+  std::lock_guard<std::mutex> lock(g_ring_mutex);
+  g_free_rings.push_back(r);
+}
 
 struct Layout {
   size_t hist_floats, gram_floats, alpha_floats, scratch_floats, floats_total;
@@ -115,9 +166,10 @@ int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi,
   if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, 1, 2, o->lam, (float)o->res_eps, stream))) return rc;
 
   // residual ring in pinned memory, one event per iteration
-  float* res_host = nullptr;
-  DEQSCI_CUDA(cudaMallocHost(&res_host, (size_t)o->max_iter * 4 * sizeof(float)));
-  std::vector<cudaEvent_t> ev(o->max_iter, nullptr);
+  ResidualRing* ring = acquire_ring(o->max_iter);
+  if (!ring) { set_error("reconstruct: pinned residual ring / events: %s", cudaGetErrorString(cudaGetLastError())); return DEQSCI_ERR_CUDA; }
+  float* res_host = ring->host;
+  std::vector<cudaEvent_t>& ev = ring->events;
   auto res_of = [&](int k) -> double {
     cudaEventSynchronize(ev[k]);
     return (double)res_host[4 * k + 1] / (o->res_eps + (double)res_host[4 * k + 2]);
@@ -134,7 +186,6 @@ int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi,
     if ((rc = deqsci_anderson_update(X, F, G, gram, alpha, res_dev, scratch, B, m, N, s, (k + 1 < m ? k + 1 : m),
                                      o->lam, (float)o->res_eps, stream))) break;
     if (cudaMemcpyAsync(res_host + 4 * k, res_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventRecord(ev[k], st) != cudaSuccess) {
       set_error("reconstruct: residual copy / event failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = DEQSCI_ERR_CUDA;
@@ -156,8 +207,7 @@ int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi,
       rc = DEQSCI_ERR_CUDA;
   }
   cudaError_t e = cudaStreamSynchronize(st);     // the pinned ring and events are released below
-  for (auto& v : ev) if (v) cudaEventDestroy(v);
-  cudaFreeHost(res_host);
+  release_ring(ring);                            // after the synchronize: nothing in flight references it
   if (rc != DEQSCI_OK) return rc;
   if (e != cudaSuccess) { set_error("reconstruct: %s", cudaGetErrorString(e)); return DEQSCI_ERR_CUDA; }
   result->residual = res;
