@@ -337,8 +337,8 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   float* bn_scale_shift = reinterpret_cast<float*>(bn_stats + (size_t)kMaxStatCtas * 2 * kHidden);   // [128]
   if (bn) {
     DEQSCI_CHECK_ARG(h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc) && tcf_supported(g.Wc),
-                     "train-mode BatchNorm path needs precision tc_split and conv images wider than 64 with even "
-                     "height (got %dx%d)", g.Hc, g.Wc);
+                     "train-mode BatchNorm path needs precision tc_split and conv images wider than 64 pixels "
+                     "(got %dx%d)", g.Hc, g.Wc);
     DEQSCI_CHECK_ARG(num_sms() <= kMaxStatCtas, "train-mode BatchNorm path: %d SMs (max %d)", num_sms(), kMaxStatCtas);
     // rows of CTAs a launch does not start stay zero (every hidden layer of this call uses the same grid)
     DEQSCI_CUDA(cudaMemsetAsync(bn_stats, 0, (size_t)kMaxStatCtas * 2 * kHidden * sizeof(double), st));

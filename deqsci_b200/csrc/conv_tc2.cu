@@ -282,9 +282,10 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     }
     for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
       const Strip s = decode(p, 2 * item + rank);
-      const bool px_valid = s.real && (s.w0 + quarter * 32 + lane) < p.Wc;
+      const bool col_valid = s.real && (s.w0 + quarter * 32 + lane) < p.Wc;
       for (int j = 0; j < p.strip_rows; ++j) {
         const int h = s.h0 + j;
+        const bool px_valid = col_valid && h < p.Hc;
         mbar_wait(bar_tfull(buf), tphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
@@ -328,7 +329,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
         if (p.debug_skip_store == 1) { if (++buf == 2) { buf = 0; tphase ^= 1; } continue; }
         if (p.debug_skip_store == 2) {             // experiment: direct global stores, no smem staging
           const int wpx = s.w0 + quarter * 32 + lane;
-          if (s.real && wpx < p.Wc) {
+          if (s.real && wpx < p.Wc && h < p.Hc) {
             const long long off = (((long long)s.nf * p.Hc + h) * p.Wc + wpx) * 64 + half * 32;
             uint4* dh = reinterpret_cast<uint4*>(p.dbg_out_hi + off);
             uint4* dl = reinterpret_cast<uint4*>(p.dbg_out_lo + off);
@@ -354,7 +355,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && s.real) {
+          if (lane == 0 && s.real && h < p.Hc) {
             tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, s.w0 + quarter * 32, h, s.nf);
             bulk_commit();
           }
@@ -429,10 +430,10 @@ void tc2_pack_weights(const float* w, uint8_t* img) {
 }
 void tc2_pack_map(int32_t* map) { tc2_layout(PackMap{map}); }
 
-// true when the pair kernel can run this shape: full 128-pixel row tiles and a strip height that divides Hc
+// true when the pair kernel can run this shape: images wider than half a 128-pixel row tile (any height)
 bool tc2_supported(int Hc, int Wc) {
   static const int enabled = env_int("DEQSCI_TC_PAIR", 1);
-  return enabled && Wc > 64 && Hc % 2 == 0;
+  return enabled && Wc > 64 && Hc >= 1;
 }
 
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
@@ -447,9 +448,10 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   // (largest power of two <= 16 dividing Hc that leaves >= n strips per SM)
   static const int rounds = env_int("DEQSCI_TC_ROUNDS", 0);
   const int R = rounds > 0 ? pick_strip_rows(NF, p.tiles_x, Hc, true, 2LL * rounds * pairs_hw, 1)
-                           : pick_strip_rows_balanced(NF, p.tiles_x, Hc, true, pairs_hw, 2, 1, 1);
+                           : pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, pairs_hw, 2, 1, 1);
   p.strip_rows = R;
-  p.strips_y = Hc / R;
+  p.strips_y = (Hc + R - 1) / R;       // the last strip of a frame may run past Hc: those rows load zeros (TMA
+                                       // out-of-bounds fill), are computed in lockstep with the pair and never stored
   p.n_strips = (long long)NF * p.tiles_x * p.strips_y;
   p.n_pair_items = (p.n_strips + 1) / 2;
   static const int skip_store = env_int("DEQSCI_TC_DEBUG_SKIP_STORE", 0);

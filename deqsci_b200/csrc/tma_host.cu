@@ -65,7 +65,7 @@ int pick_strip_rows_balanced(int NF, int tiles_x, int Hc, bool must_divide, int 
                              int overhead_half_rows, int min_rows) {
   int best = min_rows;
   long long best_cost = -1;
-  for (int R = 16; R >= min_rows; R /= 2) {
+  for (int R = 16; R >= min_rows; --R) {               // every height, not only powers of two
     if (must_divide && Hc % R != 0) continue;
     const long long strips = (long long)NF * tiles_x * ((Hc + R - 1) / R);
     const long long items = (strips + strips_per_item - 1) / strips_per_item;

@@ -138,12 +138,12 @@ class FFDNet(nn.Module, NativePlanCache):
 
     def native_train_ok(self, z):
         """Train-mode forward solve (no_grad) on the native kernels: cube [B,H,W,T] whose half-resolution
-        frames are wider than 64 pixels with even height (the CTA-pair conv kernel's tiles)."""
+        frames are wider than 64 pixels (the CTA-pair conv kernel's tiles)."""
         from ...native import default_precision
         H, W = int(z.shape[1]), int(z.shape[2])
         return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.num_input_channels == 1
                 and (getattr(self, "precision", None) or default_precision()) == "tc_split"
-                and H % 2 == 0 and W % 2 == 0 and W // 2 > 64 and (H // 2) % 2 == 0)
+                and H % 2 == 0 and W % 2 == 0 and W // 2 > 64)
 
     def uses_native(self, x):
         # train mode means batch-statistics BatchNorm (and running-stat updates) on every call, which

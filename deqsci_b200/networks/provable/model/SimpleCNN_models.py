@@ -61,7 +61,7 @@ class DnCNN(nn.Module, NativePlanCache):
         return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.channels == 1 and plain
                 and any(isinstance(m, nn.BatchNorm2d) for m in self.dncnn)
                 and (getattr(self, "precision", None) or default_precision()) == "tc_split"
-                and W > 64 and H % 2 == 0)
+                and W > 64)
 
     def _stateless_in_train_mode(self):
         return all(isinstance(m, (nn.Conv2d, nn.ReLU)) for m in self.dncnn)

@@ -138,8 +138,8 @@ int deqsci_iterate(const deqsci_denoiser* h, const float* z, const float* y, con
  * gamma, beta (may be NULL = 1 / 0) and to running_mean / running_var, which are UPDATED in place with
  * `momentum` exactly once per call, like PyTorch (unbiased variance; the caller increments
  * num_batches_tracked).  Per BatchNorm layer: conv with per-channel sum / sum-of-squares epilogue,
- * a 64-thread finalize kernel, an in-place normalise + ReLU pass.  Needs precision TC_SPLIT and conv
- * images wider than 64 pixels with even height. */
+ * a finalize kernel, an in-place normalise + ReLU pass.  Needs precision TC_SPLIT and conv images wider
+ * than 64 pixels. */
 typedef struct {
   const float* gamma;
   const float* beta;
