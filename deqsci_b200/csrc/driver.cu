@@ -4,6 +4,8 @@
 // C++ loop.  No per-iteration host round trip stalls the device: every iteration's residual lands in
 // pinned host memory through a 16-byte async copy + event, and the host tests iteration k-1 while
 // iteration k is already queued (rolling back one speculative sigma step on convergence).
+// The same loop serves the train-mode forward solve (deqsci_reconstruct_train) and the backward solve of
+// the implicit-differentiation hook (deqsci_adjoint_solve).
 #include <mutex>
 #include <vector>
 
@@ -101,7 +103,7 @@ namespace {
 //   h, bn            : f = the iterate map in train mode (deqsci_iterate_train)
 //   h == nullptr     : f(v) = gap_vjp(v) + adjoint_grad, the backward fixed-point map of tag 'ffdnet'
 //                      (solvers/new_equilibrium_utils_yaping.py:274-277); y is unused
-int reconstruct_impl(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
+int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
                      const float* x0, float* out, const deqsci_solver_opts* o, const deqsci_bn_params* bn,
                      float momentum, float eps, const float* adjoint_grad, void* workspace,
                      size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
@@ -225,7 +227,7 @@ extern "C" int deqsci_reconstruct(const deqsci_denoiser* h, const float* y, cons
                                   size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
                                   void* stream) {
   DEQSCI_CHECK_ARG(h != nullptr, "reconstruct: null denoiser handle");
-  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, nullptr, 0.f, 0.f, nullptr, workspace, workspace_bytes, result,
+  return anderson_loop(h, y, phi, phi_sum, x0, out, o, nullptr, 0.f, 0.f, nullptr, workspace, workspace_bytes, result,
                           B, H, W, T, stream);
 }
 
@@ -236,7 +238,7 @@ extern "C" int deqsci_reconstruct_train(const deqsci_denoiser* h, const float* y
                                         deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
   DEQSCI_CHECK_ARG(bn != nullptr, "reconstruct_train: null BatchNorm table");
   DEQSCI_CHECK_ARG(h != nullptr, "reconstruct_train: null denoiser handle");
-  return reconstruct_impl(h, y, phi, phi_sum, x0, out, o, bn, momentum, eps, nullptr, workspace, workspace_bytes, result,
+  return anderson_loop(h, y, phi, phi_sum, x0, out, o, bn, momentum, eps, nullptr, workspace, workspace_bytes, result,
                           B, H, W, T, stream);
 }
 
@@ -246,6 +248,6 @@ extern "C" int deqsci_adjoint_solve(const float* grad, const float* phi, const f
   DEQSCI_CHECK_ARG(grad != nullptr && o != nullptr, "adjoint_solve: null pointer");
   deqsci_solver_opts opts = *o;
   opts.final_call = 0;                 // the reference returns the solver's iterate, not one more evaluation
-  return reconstruct_impl(nullptr, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
+  return anderson_loop(nullptr, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
                           workspace_bytes, result, B, H, W, T, stream);
 }
