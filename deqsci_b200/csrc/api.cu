@@ -345,9 +345,9 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   }
   const Layer& L0 = h->layers[0];
   if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
-    // tensor-core first layer: GAP + unshuffle + split into 16-channel planes (parked in the second
+    // tensor-core first layer: GAP + unshuffle + split into 8-channel planes (parked in the second
     // ping-pong buffer, which is free until the first hidden layer writes it), then the MMA kernel
-    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * 16;
+    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * kPrepChannels;
     rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap, st);
     if (rc) return rc;
     rc = conv_first_tc_launch(act[1], in_plane, act[0], g.plane_elems, L0.w_tc, L0.scale, L0.bias, L0.relu, g.NF,

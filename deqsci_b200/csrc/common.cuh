@@ -95,6 +95,7 @@ int env_int(const char* name, int dflt);
 // bits (this split reproduces the fp32 trajectory at its noise floor) in exactly
 // the operand format the tcgen05 kind::f16 MMA consumes.
 constexpr int kHidden = 64;
+constexpr int kPrepChannels = 8;              // channels stored per pixel in the first layer's input planes (<= 5 used)
 constexpr int kMaxBnLayers = 32;              // conv layers a train-mode driver call can snapshot
 
 // bn_train.cu / api.cu helpers used by the driver

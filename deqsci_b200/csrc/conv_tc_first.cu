@@ -1,8 +1,8 @@
 // Kernel group 2d: the FIRST conv layer of the denoiser on tensor cores (split-fp16 precision).
 //
-// Input: the 16-channel planes written by gap_prep_kernel (gap.cu): channels-last [frames,Hc,Wc,16],
-// FFDNet = {sigma, 4 unshuffled sub-pixels, 0 x 11}, DnCNN = {pixel, 0 x 15}.  K per tap is padded to
-// one UMMA_K (16), so a tile costs 9 taps x (N=128 + N=64) = 864 MMA cycles instead of the 2880 FMA
+// Input: the 8-channel planes written by gap_prep_kernel (gap.cu): channels-last [frames,Hc,Wc,8],
+// FFDNet = {sigma, 4 unshuffled sub-pixels, 0 x 3}, DnCNN = {pixel, 0 x 7}; the TMA box asks for 16 channels
+// and the missing 8 arrive as zeros (out-of-bounds fill).  K per tap is thus padded to one UMMA_K (16), so a tile costs 9 taps x (N=128 + N=64) = 864 MMA cycles instead of the 2880 FMA
 // cycles per pixel-row the CUDA-core kernel needs, and the K = 45 / 9 gather disappears: a tap is a
 // UMMA descriptor 32 bytes (one pixel) further into a TMA-loaded input row (32-byte swizzle).
 //
@@ -269,7 +269,7 @@ bool tcf_supported(int Wc) {
   return enabled && Wc > 64;
 }
 
-// planes_in: [2][NF,Hc,Wc,16] fp16 (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
+// planes_in: [2][NF,Hc,Wc,8] fp16 (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
                          int Wc, cudaStream_t st) {
@@ -283,8 +283,8 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
   int rc;
-  if ((rc = make_plane_map(&in_hi, planes_in, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
-  if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, 16, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
+  if ((rc = make_plane_map(&in_hi, planes_in, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
+  if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
   if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM

@@ -180,7 +180,7 @@ extern "C" int deqsci_gap_vjp(const float* v, const float* phi, const float* phi
 
 // ------------------------------------------------------------------------------------------------
 // Prologue of the tensor-core first conv layer: (optional) GAP step, then the frame-major,
-// channels-last 16-channel input planes that conv_tc_first.cu loads with TMA.
+// channels-last 8-channel input planes that conv_tc_first.cu loads with TMA (as 16: out-of-bounds fill).
 //   FFDNet: one thread per half-resolution pixel (b,i,j): z' of its 2x2 fine pixels for all T frames,
 //           plane row [b*T+t, i, j, :] = {sigma, z'(0,0), z'(0,1), z'(1,0), z'(1,1), 0 x 11}
 //           (pixel-unshuffle + noise map of networks/ffdnet/functions.py:16-53; because sigma is a real
@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__
       }
     }
     for (int t = 0; t < T; ++t) {
-      __align__(16) __half hi[16];
-      __align__(16) __half lo[16];
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { hi[c] = __float2half_rn(0.f); lo[c] = hi[c]; }
+      for (int c = 0; c < 8; ++c) { hi[c] = __float2half_rn(0.f); lo[c] = hi[c]; }
       if (KIND == DEQSCI_NET_FFDNET) { hi[0] = s_hi; lo[0] = s_lo; }
 #pragma unroll
       for (int s = 0; s < NSUB; ++s) {
@@ -239,13 +239,9 @@ __global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__
         const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
         split_f16(v, hi[c], lo[c]);
       }
-      const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * 16;
-      uint4* dh = reinterpret_cast<uint4*>(planes + row);
-      uint4* dl = reinterpret_cast<uint4*>(planes + plane_elems + row);
-      dh[0] = reinterpret_cast<const uint4*>(hi)[0];
-      dh[1] = reinterpret_cast<const uint4*>(hi)[1];
-      dl[0] = reinterpret_cast<const uint4*>(lo)[0];
-      dl[1] = reinterpret_cast<const uint4*>(lo)[1];
+      const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * kPrepChannels;
+      *reinterpret_cast<uint4*>(planes + row) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(planes + plane_elems + row) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }
@@ -314,18 +310,15 @@ __global__ void __launch_bounds__(128) gap_prep_t8_kernel(const float* __restric
         const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
         split_f16(zv[s][t], hi[c], lo[c]);
       }
-      const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * 16;
-      uint4* dh = reinterpret_cast<uint4*>(planes + row);
-      uint4* dl = reinterpret_cast<uint4*>(planes + plane_elems + row);
-      dh[0] = *reinterpret_cast<const uint4*>(hi);
-      dh[1] = make_uint4(0u, 0u, 0u, 0u);
-      dl[0] = *reinterpret_cast<const uint4*>(lo);
-      dl[1] = make_uint4(0u, 0u, 0u, 0u);
+      const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * kPrepChannels;
+      *reinterpret_cast<uint4*>(planes + row) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(planes + plane_elems + row) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }
 
-// planes: [2][B*T, Hc, Wc, 16] fp16; plane_elems = B*T*Hc*Wc*16.  y/phi/phi_sum/zprime_out may be null
+// planes: [2][B*T, Hc, Wc, 8] fp16 (kPrepChannels; the first layer's TMA box asks for 16 channels and gets zeros for
+// the missing 8: out-of-bounds fill); plane_elems = B*T*Hc*Wc*8.  y/phi/phi_sum/zprime_out may be null
 // when do_gap == 0 (the planes are then built from z itself).
 int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
                     float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
