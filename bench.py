@@ -263,6 +263,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
+    # latency mode (how the reference itself runs its benchmark: one measurement at a time), reported beside
+    # the throughput numbers; single-GPU runs only
+    lat_ms = None
+    if world == 1 and B > 1:
+        y1, p1 = y_d[:1].contiguous(), phi_d[:1].contiguous()
+        for _ in range(2):
+            reconstruct(deq, y1, p1)
+        lat_ms = timed(lambda: reconstruct(deq, y1, p1), 3) / 3
+
     if rank != 0:
         return
     peaks, peak_src = measured_peaks()
@@ -314,6 +323,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         "kernels": shares,
         "check": {"finite": finite, "psnr_vs_synthetic_gt_db": psnr},
     }
+    if lat_ms is not None:
+        line["latency_batch1"] = {"ms_per_recon": lat_ms, "recon_per_s": 1e3 / lat_ms,
+                                  "note": "same call at batch 1 (the reference's own test mode), inputs resident"}
     if world == 1 and not args.no_cpu_baseline and args.denoiser == "ffdnet":
         v, dt, per_call = cpu_port_recon_per_s(args.cpu_iters, y_h, phi_h)
         line["cpu_baseline"] = {"value": v, "unit": "recon/s", "cores": os.cpu_count(), "kind": "port",
