@@ -662,6 +662,28 @@ def test_error_paths_on_device(dev):
                      torch.rand(1, 16, 16, device=dev), 0.1)                 # inconsistent shapes
 
 
+def test_integration_md_binding_stub_runs(dev):
+    """The ctypes stub INTEGRATION.md tells a reference maintainer to paste into utils/cg_utils.py is executed
+    as written (only the library path is made absolute) and must agree bit for bit with the package's own
+    A_torch_ / At_torch_."""
+    import re
+    from conftest import ROOT
+    from deqsci_b200 import _lib
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "def A_torch_(x, Phi):" in b and "ctypes.CDLL" in b)
+    stub = stub.replace('ctypes.CDLL("libdeqsci.so")', "ctypes.CDLL(%r)" % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 24, 40, 8, generator=g).to(dev)
+    Phi = (torch.rand(2, 24, 40, 8, generator=g) < 0.5).float().to(dev)
+    y = ns["A_torch_"](x, Phi)
+    assert torch.equal(y, A_torch_(x, Phi))
+    assert torch.equal(ns["At_torch_"](y, Phi), At_torch_(y, Phi))
+
+
 # ---------------------------------------------------------------------------------------------
 # (9) the entry script with the reference's flags, on .mat files and a .ckpt in the reference's formats
 # ---------------------------------------------------------------------------------------------
