@@ -37,7 +37,7 @@ int conv_tc_launch(int mode, bool split, const __half* act_in, __half* act_out, 
                    const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
 int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
                     float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
-                    int T, bool do_gap, cudaStream_t st);
+                    int T, bool do_gap, bool zprime_planar, cudaStream_t st);
 size_t tcf_weight_image_bytes();
 void tcf_pack_weights(const float* w, int cin, uint8_t* img);
 void tcf_pack_map(int cin, int32_t* map);
@@ -51,7 +51,7 @@ void tcl_pack_map(int cout, int32_t* map);
 bool tcl_supported(int Wc);
 int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, const uint8_t* wimg,
                         const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                        const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st);
+                        const float* zprime, bool zprime_planar, float* out_cube, int H, int W, int T, cudaStream_t st);
 size_t tc2_weight_image_bytes();
 void tc2_pack_weights(const float* w, uint8_t* img);
 void tc2_pack_map(int32_t* map);
@@ -344,11 +344,15 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     DEQSCI_CUDA(cudaMemsetAsync(bn_stats, 0, (size_t)kMaxStatCtas * 2 * kHidden * sizeof(double), st));
   }
   const Layer& L0 = h->layers[0];
+  // z' goes from gap_prep straight to the tensor-core last layer: frame-planar [B,T,H,W] suits both (the last
+  // layer handles one frame per tile); every other producer / consumer keeps the cube layout [B,H,W,T]
+  const bool zprime_planar = fuse_gap && h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc) && tcl_supported(g.Wc);
   if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
     // tensor-core first layer: GAP + unshuffle + split into 8-channel planes (parked in the second
     // ping-pong buffer, which is free until the first hidden layer writes it), then the MMA kernel
     const long long in_plane = (long long)g.NF * g.Hc * g.Wc * kPrepChannels;
-    rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap, st);
+    rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap,
+                         zprime_planar, st);
     if (rc) return rc;
     rc = conv_first_tc_launch(act[1], in_plane, act[0], g.plane_elems, L0.w_tc, L0.scale, L0.bias, L0.relu, g.NF,
                               g.Hc, g.Wc, st);
@@ -383,7 +387,7 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   const Layer& LL = h->layers[nl - 1];
   if (h->precision != DEQSCI_PREC_FP32 && tcl_supported(g.Wc))
     return conv_last_tc_launch(LL.cout, act[cur], g.plane_elems, LL.w_tc2, LL.scale, LL.bias, LL.relu, g.NF, g.Hc,
-                               g.Wc, fuse_gap ? zprime_ws : z, out, H, W, T, st);
+                               g.Wc, fuse_gap ? zprime_ws : z, zprime_planar, out, H, W, T, st);
   if (h->precision != DEQSCI_PREC_FP32)
     return conv_tc_launch(h->kind == DEQSCI_NET_FFDNET ? 1 : 2, h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], nullptr,
                           g.plane_elems, LL.w_tc, LL.scale, LL.bias, LL.relu, g.NF, g.Hc, g.Wc,

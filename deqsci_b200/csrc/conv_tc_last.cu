@@ -52,6 +52,7 @@ struct Params {
   float* out_cube;
   int H, W, T;
   int bufs;                   // accumulator buffers in use (4..kBufs)
+  int zp_planar;              // z' is frame-planar [B,T,H,W] (written by gap_prep for this kernel) instead of [B,H,W,T]
 };
 struct Item { int nf, h0, w0, ntiles; };
 
@@ -191,7 +192,24 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
         for (int c = 0; c < COUT; ++c) {
           if (COUT == 4) gidx[c] = (((long long)b * p.H + 2 * h + (c >> 1)) * p.W + 2 * w + (c & 1)) * p.T + t;
           else           gidx[c] = (((long long)b * p.H + h) * p.W + w) * p.T + t;
-          zp[c] = (w < p.Wc) ? __ldg(p.zprime + gidx[c]) : 0.f;
+        }
+        if (p.zp_planar) {
+          // frame-planar z': this lane's sub-pixels are two adjacent pairs, the warp's loads are contiguous
+          if (COUT == 4) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const float2 v = (w < p.Wc) ? __ldg(reinterpret_cast<const float2*>(
+                                                p.zprime + (((long long)b * p.T + t) * p.H + 2 * h + dy) * p.W + 2 * w))
+                                          : make_float2(0.f, 0.f);
+              zp[(dy * 2) % COUT] = v.x;
+              zp[(dy * 2 + 1) % COUT] = v.y;
+            }
+          } else {
+            zp[0] = (w < p.Wc) ? __ldg(p.zprime + (((long long)b * p.T + t) * p.H + h) * p.W + w) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) zp[c] = (w < p.Wc) ? __ldg(p.zprime + gidx[c]) : 0.f;
         }
         while (rows_ready < j + 3) {
           const uint32_t g = g0 + rows_ready;
@@ -273,7 +291,8 @@ bool tcl_supported(int Wc) {
 
 int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, const uint8_t* wimg,
                         const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                        const float* zprime, float* out_cube, int H, int W, int T, cudaStream_t st) {
+                        const float* zprime, bool zprime_planar, float* out_cube, int H, int W, int T,
+                        cudaStream_t st) {
   tcl::Params p;
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
@@ -283,6 +302,7 @@ int conv_last_tc_launch(int cout, const __half* act_in, long long plane_elems, c
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
   p.zprime = zprime; p.out_cube = out_cube; p.H = H; p.W = W; p.T = T;
+  p.zp_planar = zprime_planar ? 1 : 0;
   static const int bufs = env_int("DEQSCI_TCL_BUFS", tcl::kBufs);
   p.bufs = bufs < 4 ? 4 : (bufs > tcl::kBufs ? tcl::kBufs : bufs);
   CUtensorMap in_hi, in_lo;

@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__
         float v = z[pix[s] * T + t];
         if (do_gap) {
           v = __fadd_rn(v, __fmul_rn(r[s], phi[pix[s] * T + t]));
-          zprime_out[pix[s] * T + t] = v;
+          if (do_gap == 2)               // planar z' [B,T,H,W] for the tensor-core last layer (coalesced there)
+            zprime_out[(((long long)b * T + t) * H + SC * i + s / SC) * W + SC * j + s % SC] = v;
+          else
+            zprime_out[pix[s] * T + t] = v;
         }
         const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
         split_f16(v, hi[c], lo[c]);
@@ -293,9 +296,23 @@ __global__ void __launch_bounds__(128) gap_prep_t8_kernel(const float* __restric
         const float r = __fdiv_rn(__fsub_rn(__ldg(y + pix[s]), __fadd_rn(lo4, hi4)), __ldg(phi_sum + pix[s]));
 #pragma unroll
         for (int t = 0; t < T; ++t) zv[s][t] = __fadd_rn(zv[s][t], __fmul_rn(r, pv[t]));
-        float4* zo = reinterpret_cast<float4*>(zprime_out + pix[s] * T);
-        zo[0] = make_float4(zv[s][0], zv[s][1], zv[s][2], zv[s][3]);
-        zo[1] = make_float4(zv[s][4], zv[s][5], zv[s][6], zv[s][7]);
+        if (do_gap == 1) {
+          float4* zo = reinterpret_cast<float4*>(zprime_out + pix[s] * T);
+          zo[0] = make_float4(zv[s][0], zv[s][1], zv[s][2], zv[s][3]);
+          zo[1] = make_float4(zv[s][4], zv[s][5], zv[s][6], zv[s][7]);
+        }
+      }
+      if (do_gap == 2) {
+        // planar z' [B,T,H,W]: what the tensor-core last layer reads back per frame -- there one lane owns one
+        // pixel of ONE frame, so the frame-innermost cube layout costs it a 32-byte sector per float
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int dy = 0; dy < SC; ++dy) {
+            float* dst = zprime_out + (((long long)b * T + t) * H + SC * i + dy) * W + SC * j;
+            if (SC == 2) *reinterpret_cast<float2*>(dst) = make_float2(zv[dy * 2][t], zv[dy * 2 + 1][t]);
+            else         *dst = zv[0][t];
+          }
       }
     }
 #pragma unroll
@@ -322,7 +339,8 @@ __global__ void __launch_bounds__(128) gap_prep_t8_kernel(const float* __restric
 // when do_gap == 0 (the planes are then built from z itself).
 int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
                     float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
-                    int T, bool do_gap, cudaStream_t st) {
+                    int T, bool do_gap_flag, bool zprime_planar, cudaStream_t st) {
+  const int do_gap = do_gap_flag ? (zprime_planar ? 2 : 1) : 0;
   const int SC = kind == DEQSCI_NET_FFDNET ? 2 : 1;
   const long long n = (long long)B * (H / SC) * (W / SC);
   long long blocks = (n + 127) / 128;
@@ -333,19 +351,19 @@ int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, 
   if (T == 8 && a16(z) && a16(phi) && a16(zprime_out)) {
     if (kind == DEQSCI_NET_FFDNET)
       DEQSCI_CUDA(launch_pdl(gap_prep_t8_kernel<DEQSCI_NET_FFDNET>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum,
-                             zprime_out, planes, plane_elems, sigma, B, H, W, (int)do_gap));
+                             zprime_out, planes, plane_elems, sigma, B, H, W, do_gap));
     else
       DEQSCI_CUDA(launch_pdl(gap_prep_t8_kernel<DEQSCI_NET_DNCNN>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum,
-                             zprime_out, planes, plane_elems, sigma, B, H, W, (int)do_gap));
+                             zprime_out, planes, plane_elems, sigma, B, H, W, do_gap));
     DEQSCI_LAUNCH_CHECK();
     return DEQSCI_OK;
   }
   if (kind == DEQSCI_NET_FFDNET)
     DEQSCI_CUDA(launch_pdl(gap_prep_kernel<DEQSCI_NET_FFDNET>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum, zprime_out,
-                           planes, plane_elems, sigma, B, H, W, T, (int)do_gap));
+                           planes, plane_elems, sigma, B, H, W, T, do_gap));
   else
     DEQSCI_CUDA(launch_pdl(gap_prep_kernel<DEQSCI_NET_DNCNN>, (unsigned)blocks, 128, 0, st, z, y, phi, phi_sum, zprime_out,
-                           planes, plane_elems, sigma, B, H, W, T, (int)do_gap));
+                           planes, plane_elems, sigma, B, H, W, T, do_gap));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }
