@@ -70,6 +70,7 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, _P]),
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
+    "deqsci_debug_pair_strip_rows": (c_int, [c_int, c_int, c_int, c_int]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),
 }
 

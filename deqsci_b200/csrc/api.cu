@@ -418,6 +418,12 @@ extern "C" int deqsci_iterate_train(const deqsci_denoiser* h, const float* z, co
                    momentum, eps);
 }
 
+// Testing hook (declared in deqsci.h): the pair kernel's strip-height choice, host arithmetic only.
+extern "C" int deqsci_debug_pair_strip_rows(int NF, int Hc, int Wc, int n_sms) {
+  if (NF <= 0 || Hc <= 0 || Wc <= 0 || n_sms < 2) return 0;
+  return pick_strip_rows_balanced(NF, (Wc + 127) / 128, Hc, false, n_sms / 2, 2, 1, 1);
+}
+
 // Testing hook (declared in deqsci.h): one hidden 64->64 layer on caller-provided planes.
 extern "C" int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* act_in, void* act_out,
                                          int NF, int Hc, int Wc, void* stream) {

@@ -265,6 +265,11 @@ int deqsci_profile_end(double* ms_sum, long long* n_sampled, long long* n_launch
 int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* act_in, void* act_out,
                               int NF, int Hc, int Wc, void* stream);
 
+/* Testing hook (host only, no device work): the strip height the CTA-pair hidden kernel picks for NF frames of
+ * Hc x Wc conv pixels on a device with `num_sms` SMs -- the cost model of csrc/tma_host.cu, so the CPU test
+ * suite can pin its choices. */
+int deqsci_debug_pair_strip_rows(int NF, int Hc, int Wc, int num_sms);
+
 #ifdef __cplusplus
 }
 #endif

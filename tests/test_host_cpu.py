@@ -188,3 +188,25 @@ def test_realsn_dncnn_train_mode_matches_reference():
             assert int(got) == int(v[k])
         else:
             assert rel(got.astype(np.float64), v[k].astype(np.float64)) <= 1e-5, k
+
+
+def test_pair_kernel_strip_height_model():
+    """Host arithmetic of the CTA-pair kernel's strip-height choice (csrc/tma_host.cu, DESIGN.md finding 11) on a
+    148-SM device: rounds x (rows + half a row of refill) is minimised, taller strips win ties, any height 1..16
+    is allowed (the last strip of a frame may run past it)."""
+    L = _lib.lib()
+
+    def cost(NF, Hc, R, pairs=74):
+        strips = NF * ((Hc + R - 1) // R)
+        rounds = -(-((strips + 1) // 2) // pairs)
+        return rounds * (2 * R + 1)
+
+    for NF, Hc in [(8, 128), (16, 128), (24, 128), (32, 128), (64, 128), (256, 128), (8, 127), (1, 5), (2048, 128)]:
+        R = L.deqsci_debug_pair_strip_rows(NF, Hc, 128, 148)
+        assert 1 <= R <= 16
+        best = min(cost(NF, Hc, r) for r in range(1, 17))
+        assert cost(NF, Hc, R) == best, (NF, Hc, R)
+        assert all(cost(NF, Hc, r) > best for r in range(R + 1, 17)), (NF, Hc, R)      # ties -> the taller strip
+    assert L.deqsci_debug_pair_strip_rows(8, 128, 128, 148) == 8          # batch 1: one round of 8-row strips
+    assert L.deqsci_debug_pair_strip_rows(256, 128, 128, 148) == 16       # batch 32
+    assert L.deqsci_debug_pair_strip_rows(0, 128, 128, 148) == 0
