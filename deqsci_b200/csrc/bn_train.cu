@@ -62,11 +62,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act,
     __half* hh = reinterpret_cast<__half*>(&h4);
     __half* ll = reinterpret_cast<__half*>(&l4);
     const int c0 = (int)((i * 8) & (kHidden - 1));
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h4);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&l4);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = fmaf(join_f16(hh[e], ll[e]), ss[c0 + e], ss[kHidden + c0 + e]);
-      if (relu) v = fmaxf(v, 0.f);
-      split_f16(v, hh[e], ll[e]);
+    for (int e = 0; e < 8; e += 2) {
+      float v0 = fmaf(join_f16(hh[e], ll[e]), ss[c0 + e], ss[kHidden + c0 + e]);
+      float v1 = fmaf(join_f16(hh[e + 1], ll[e + 1]), ss[c0 + e + 1], ss[kHidden + c0 + e + 1]);
+      if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+      split_f16x2(v0, v1, hp[e >> 1], lp[e >> 1]);
     }
     *reinterpret_cast<uint4*>(act + i * 8) = h4;
     *reinterpret_cast<uint4*>(act + plane_elems + i * 8) = l4;

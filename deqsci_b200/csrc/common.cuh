@@ -108,6 +108,16 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
 }
+// Two values at once with the packed conversion (cvt.rn.f16x2.f32 = F2FP, a full-rate ALU instruction; the scalar
+// cvt.rn.f16.f32 is a quarter-rate F2F and was 64 of ~480 instructions per epilogue tile).  Same roundings as
+// split_f16; packs v0 into the low half, as the activation planes want consecutive channels.
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi_pk, uint32_t& lo_pk) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((v0 - hf.x) * kLoScale, (v1 - hf.y) * kLoScale);
+  hi_pk = *reinterpret_cast<const uint32_t*>(&h);
+  lo_pk = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float join_f16(__half hi, __half lo) {
   return fmaf(__half2float(lo), kLoInvScale, __half2float(hi));
 }

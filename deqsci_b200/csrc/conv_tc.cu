@@ -338,11 +338,7 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             a = fmaf(a, aff_s[c], aff_s[64 + c]);
             v[u] = p.relu ? fmaxf(a, 0.f) : a;
           }
-          __half h0, l0, h1, l1;
-          split_f16(v[0], h0, l0);
-          split_f16(v[1], h1, l1);
-          hi_pk[e >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          lo_pk[e >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          split_f16x2(v[0], v[1], hi_pk[e >> 1], lo_pk[e >> 1]);
         }
         if (inside) {
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off + half * 32);
@@ -356,7 +352,7 @@ conv_mid_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(buf));    // 4 arrivals (one per epilogue warp) free the buffer
+      if (elect_one_sync()) mbar_arrive(bar_tempty(buf));    // 4 arrivals (one per epilogue warp) free the buffer
       if (++buf == 2) { buf = 0; tphase ^= 1; }
      }
     }

@@ -312,17 +312,14 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
                 st_sq[part * 16 + i + u] = fmaf(v[u], v[u], st_sq[part * 16 + i + u]);
               }
             }
-            __half h0, l0, h1, l1;
-            split_f16(v[0], h0, l0);
-            split_f16(v[1], h1, l1);
-            hi_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo_pk[part * 8 + (i >> 1)] = ((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16)) & p.lo_mask;
+            split_f16x2(v[0], v[1], hi_pk[part * 8 + (i >> 1)], lo_pk[part * 8 + (i >> 1)]);
+            lo_pk[part * 8 + (i >> 1)] = lo_pk[part * 8 + (i >> 1)] & p.lo_mask;
           }
         }
         // accumulator drained: hand the TMEM buffer back to the leader's MMA thread
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(buf == 0 ? tempty_leader0 : tempty_leader1);
+        if (elect_one_sync()) mbar_arrive_cluster(buf == 0 ? tempty_leader0 : tempty_leader1);
         // stage (64-byte swizzle: chunk ^= (row >> 1) & 3) and store the two planes with TMA
         const uint32_t row_addr = stage + lane * 64;
         const int sw = (lane >> 1) & 3;
@@ -345,7 +342,8 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
-          if (lane == 0) bulk_wait_read0();          // previous store has finished reading the staging buffer
+          bulk_wait_read0();      // previous store has finished reading the staging buffer (all lanes execute it;
+                                  // only the storing lane has a group pending -- no lane-0 guard, see conv_tc_first.cu)
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -355,15 +353,17 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && s.real && h < p.Hc) {
-            tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, s.w0 + quarter * 32, h, s.nf);
-            bulk_commit();
+          if (s.real && h < p.Hc) {
+            if (elect_one_sync()) {
+              tma_store_4d(plane == 0 ? &out_hi : &out_lo, stage, half * 32, s.w0 + quarter * 32, h, s.nf);
+              bulk_commit();
+            }
           }
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
     }
-    if (lane == 0) bulk_wait0();
+    bulk_wait0();
     if (STATS) {
       // warp totals of this warp's 32 channels -> its (now idle) staging buffer: [0,32) sums, [32,64) squares
       float* mine = reinterpret_cast<float*>(st_s + e * kStageBytes);

@@ -31,7 +31,7 @@ constexpr int kSlotBytes = 2 * kPlaneBytes;
 constexpr int kTxBytes = 2 * (kTileM + 2) * kRowBytes;
 constexpr int kTapBytesB = 128 * kRowBytes;                    // [Wh | Wl'] rows x 16 k
 constexpr int kWBytes = 9 * kTapBytesB;                        // 36 KB
-constexpr int kStageBytes = 4096;                              // per epilogue warp: hi and lo staging, 32 px x 32 ch each
+constexpr int kStageBytes = 4096;                              // one staging tile: 32 px x 64 ch fp16 (per warp pair: hi tile, lo tile)
 constexpr int kAccCols = 128;
 constexpr int kTmemCols = 256;
 constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
@@ -170,7 +170,11 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
     const int e = warp - 2;
     const int quarter = warp & 3;
     const int half = e >> 2;
-    const uint32_t stage = smem_u32(st_s + e * kStageBytes);
+    // the two warps that own the same 32 pixels (channel halves 0 / 1) share one staging tile per plane --
+    // [32 px][128 B], 128-byte swizzle -- so a TMA store moves whole 128-byte pixels: with 64-byte rows the
+    // store engine's request rate (one row per request) capped this kernel at ~12 B/clk/SM
+    const int pair = e & 3;
+    const uint32_t stage = smem_u32(st_s + pair * 2 * kStageBytes);
     int buf = 0;
     uint32_t tphase = 0;
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -197,41 +201,43 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
               a = fmaf(a, aff_s[c], aff_s[64 + c]);
               v[u] = p.relu ? fmaxf(a, 0.f) : a;
             }
-            __half h0, l0, h1, l1;
-            split_f16(v[0], h0, l0);
-            split_f16(v[1], h1, l1);
-            hi_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo_pk[part * 8 + (i >> 1)] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            split_f16x2(v[0], v[1], hi_pk[part * 8 + (i >> 1)], lo_pk[part * 8 + (i >> 1)]);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(buf));
-        const uint32_t row_addr = stage + lane * 64;
-        const int sw = (lane >> 1) & 3;
-        if (lane == 0) bulk_wait_read0();          // the previous tile's two stores have read the staging buffers
-        __syncwarp();
+        if (elect_one_sync()) mbar_arrive(bar_tempty(buf));
+        const uint32_t row_addr = stage + lane * 128;
+        const int sw = lane & 7;
+        // the previous tile's stores (issued by the half-0 warp) have read the staging tiles; every lane executes
+        // the wait (only the issuing lane has a bulk group pending): no lane-0 guard, which ptxas would wrap in a
+        // per-lane uniformisation loop (BRA.U.ANY)
+        if (half == 0) bulk_wait_read0();
+        named_bar_sync(1 + pair, 64);
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
           const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + plane * 2048 + ((q ^ sw) << 4)),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + plane * kStageBytes +
+                                                                          (((half * 4 + q) ^ sw) << 4)),
                          "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                          : "memory");
           }
         }
         fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&out_hi, stage, half * 32, it.w0 + quarter * 32, h, it.nf);
-          tma_store_4d(&out_lo, stage + 2048, half * 32, it.w0 + quarter * 32, h, it.nf);
-          bulk_commit();
+        named_bar_sync(1 + pair, 64);
+        if (half == 0) {
+          if (elect_one_sync()) {
+            tma_store_4d(&out_hi, stage, 0, it.w0 + quarter * 32, h, it.nf);
+            tma_store_4d(&out_lo, stage + kStageBytes, 0, it.w0 + quarter * 32, h, it.nf);
+            bulk_commit();
+          }
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
     }
-    if (lane == 0) bulk_wait0();
+    bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -285,8 +291,8 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   int rc;
   if ((rc = make_plane_map(&in_hi, planes_in, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
   if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
-  if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
-  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
+  if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
+  if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
   const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM
   DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    tcf::kSmemBytes));

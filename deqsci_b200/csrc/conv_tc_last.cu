@@ -228,7 +228,7 @@ conv_last_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_cons
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           mbar_arrive(bar_tempty((g0 + j) % nb));              // V_j is dead after output row j
           if (j == it.ntiles - 1) {                               // end of strip: its last two rows too
             mbar_arrive(bar_tempty((g0 + j + 1) % nb));

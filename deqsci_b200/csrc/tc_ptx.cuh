@@ -12,6 +12,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // One lane of a converged warp.  ptxas knows a region guarded by elect.sync has a single active
 // thread, so tcgen05 / TMA descriptor operands move to uniform registers directly (guarding with
 // `lane == 0` wraps every such instruction in an ELECT/R2UR.BROADCAST/BRA.U.ANY loop).
+// named barrier among `threads` threads (a multiple of 32); id 0 is __syncthreads'
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(
