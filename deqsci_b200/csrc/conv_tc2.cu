@@ -174,8 +174,8 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) {
     const int c = threadIdx.x - 64;
-    aff_s[c] = p.scale ? p.scale[c] : 1.f;
-    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+    aff_s[2 * c] = p.scale ? p.scale[c] : 1.f;          // {scale, bias} pairs: one 16-byte load per two channels
+    aff_s[2 * c + 1] = p.bias ? p.bias[c] : 0.f;
   }
   if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), kTmemCols);
   if (warp == 0 && elect_one_sync()) {
@@ -300,12 +300,13 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float v[2];
+            const float4 sb4 = *reinterpret_cast<const float4*>(aff_s + 2 * (half * 32 + part * 16 + i));
+            const float sb[4] = {sb4.x, sb4.y, sb4.z, sb4.w};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const int c = half * 32 + part * 16 + i + u;
               float a = fmaf(__uint_as_float(c1[i + u]) + __uint_as_float(c2[i + u]), kLoInvScale,
                              __uint_as_float(acc[i + u]));
-              a = fmaf(a, aff_s[c], aff_s[64 + c]);
+              a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
               v[u] = p.relu ? fmaxf(a, 0.f) : a;
               if (STATS && px_valid) {
                 st_sum[part * 16 + i + u] += v[u];

@@ -59,6 +59,9 @@ __device__ __forceinline__ Item decode(const Params& p, long long item) {
   return it;
 }
 
+// AFFINE = false: the layer has no folded scale / bias (FFDNet's and DnCNN's first layers: conv + ReLU), so the
+// epilogue skips the per-channel multiply-add and its shared-memory loads
+template <bool AFFINE>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
                      const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
@@ -89,8 +92,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) {
     const int c = threadIdx.x - 64;
-    aff_s[c] = p.scale ? p.scale[c] : 1.f;
-    aff_s[64 + c] = p.bias ? p.bias[c] : 0.f;
+    aff_s[2 * c] = p.scale ? p.scale[c] : 1.f;          // {scale, bias} pairs
+    aff_s[2 * c + 1] = p.bias ? p.bias[c] : 0.f;
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
@@ -194,11 +197,15 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float v[2];
+            float sb[4] = {1.f, 0.f, 1.f, 0.f};
+            if (AFFINE) {
+              const float4 sb4 = *reinterpret_cast<const float4*>(aff_s + 2 * (half * 32 + part * 16 + i));
+              sb[0] = sb4.x; sb[1] = sb4.y; sb[2] = sb4.z; sb[3] = sb4.w;
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const int c = half * 32 + part * 16 + i + u;
               float a = fmaf(__uint_as_float(cor[i + u]), kLoInvScale, __uint_as_float(acc[i + u]));
-              a = fmaf(a, aff_s[c], aff_s[64 + c]);
+              if (AFFINE) a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
               v[u] = p.relu ? fmaxf(a, 0.f) : a;
             }
             split_f16x2(v[0], v[1], hi_pk[part * 8 + (i >> 1)], lo_pk[part * 8 + (i >> 1)]);
@@ -294,11 +301,18 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
   const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM
-  DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   tcf::kSmemBytes));
   ProfScope prof(PK_CONV_FIRST, st);
-  DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi, in_lo, out_hi,
-                         out_lo, p));
+  if (scale || bias) {
+    DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tcf::kSmemBytes));
+    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<true>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi,
+                           in_lo, out_hi, out_lo, p));
+  } else {
+    DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tcf::kSmemBytes));
+    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<false>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi,
+                           in_lo, out_hi, out_lo, p));
+  }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }
