@@ -40,6 +40,20 @@ def make_conv(mode):
     def conv3x3(x, w):
         x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
         w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+        if mode == "first_kpack":
+            # hidden layers as the product runs them (3-product split); the FIRST layer with the K-packing idea of
+            # [Ah | Ah | Al'] against [Wh | Wl | Wh * 2^-11], correction weights at true scale
+            # in fp16 (subnormals included), everything in one accumulator
+            ah, wh = q(x, torch.float16), q(w, torch.float16)
+            al = q((x - ah) * S, torch.float16)
+            if x.shape[1] == 64 and w.shape[0] == 64:
+                wl = q((w - wh) * S, torch.float16)
+                return (conv(ah, wh) + (conv(ah, wl) + conv(al, wh)) / S).numpy()
+            if w.shape[0] == 64:                      # first layer (cin = 5 or 1)
+                wl_true = q(w - wh, torch.float16)
+                wh_small = q(wh / S, torch.float16)
+                return (conv(ah, wh) + conv(ah, wl_true) + conv(al, wh_small)).numpy()
+            return conv(x, w).numpy()
         if mode == "fp32" or x.shape[1] != 64 or w.shape[0] != 64:
             return conv(x, w).numpy()
         ah, wh = q(x, torch.float16), q(w, torch.float16)
