@@ -203,15 +203,10 @@ __global__ void repack_kernel(const float* __restrict__ w, const int32_t* __rest
   if (i >= n) return;
   const int32_t m = map[i];
   if (as_f32) {
-    reinterpret_cast<float*>(dst)[i] = m < 0 ? 0.f : w[m >> 1];
+    reinterpret_cast<float*>(dst)[i] = m < 0 ? 0.f : w[m >> 2];
     return;
   }
-  __half out = __float2half_rn(0.f);
-  if (m >= 0) {
-    __half hi, lo;
-    split_f16(w[m >> 1], hi, lo);
-    out = (m & 1) ? lo : hi;
-  }
+  const __half out = m >= 0 ? pack_half(w[m >> 2], m & 3) : __float2half_rn(0.f);
   reinterpret_cast<__half*>(dst)[i] = out;
 }
 
@@ -243,7 +238,7 @@ int build_layer_maps(deqsci_denoiser* h, int i) {
   if ((rc = get_map(h, key, L.n_cc, [&](int32_t* m) {
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < cin; ++c)
-            for (int t = 0; t < 9; ++t) m[(t * cin + c) * cout + o] = 2 * ((o * cin + c) * 9 + t);
+            for (int t = 0; t < 9; ++t) m[(t * cin + c) * cout + o] = 4 * ((o * cin + c) * 9 + t);
       }, &L.map_cc))) return rc;
   if (L.w_tc && i == 0) {
     L.n_tc = (int)(tcf_weight_image_bytes() / 2);
@@ -348,9 +343,9 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   // layer handles one frame per tile); every other producer / consumer keeps the cube layout [B,H,W,T]
   const bool zprime_planar = fuse_gap && h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc) && tcl_supported(g.Wc);
   if (h->precision != DEQSCI_PREC_FP32 && tcf_supported(g.Wc)) {
-    // tensor-core first layer: GAP + unshuffle + split into 8-channel planes (parked in the second
+    // tensor-core first layer: GAP + unshuffle + K-packing into one 16-channel plane (parked in the second
     // ping-pong buffer, which is free until the first hidden layer writes it), then the MMA kernel
-    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * kPrepChannels;
+    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * kPrepChannels;      // ONE plane: [Ah | Ah | Al']
     rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap,
                          zprime_planar, st);
     if (rc) return rc;

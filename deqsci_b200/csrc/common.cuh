@@ -95,7 +95,7 @@ int env_int(const char* name, int dflt);
 // bits (this split reproduces the fp32 trajectory at its noise floor) in exactly
 // the operand format the tcgen05 kind::f16 MMA consumes.
 constexpr int kHidden = 64;
-constexpr int kPrepChannels = 8;              // channels stored per pixel in the first layer's input planes (<= 5 used)
+constexpr int kPrepChannels = 16;             // the first layer's input plane: one K = 16 row per pixel, [Ah | Ah | Al' | 0]
 constexpr int kMaxBnLayers = 32;              // conv layers a train-mode driver call can snapshot
 
 // bn_train.cu / api.cu helpers used by the driver
@@ -123,21 +123,30 @@ __device__ __forceinline__ float join_f16(__half hi, __half lo) {
 }
 
 // The weight images (shared-memory operand layouts of the tensor-core kernels) are written through an
-// emitter -- emit(byte offset in the image, index into the [cout][cin][3][3] weights, hi or lo' half) -- so one
+// emitter -- emit(byte offset in the image, index into the [cout][cin][3][3] weights, kind of half) -- so one
 // layout routine serves the host packer (PackWrite) and the gather map of the device-side repack
-// (PackMap: element -> 2*index + is_lo, -1 = zero padding; deqsci_denoiser_update_weights).
+// (PackMap: element -> 4*index + kind, -1 = zero padding; deqsci_denoiser_update_weights).
+// Kinds: 0 = hi(w), 1 = lo'(w) = (w - hi) * 2^11, 2 = the low part at its true scale (w - hi), 3 = hi * 2^-11
+// (kinds 2 and 3 live in fp16's subnormal range: the K-packed first layer, conv_tc_first.cu).
+enum { kPackHi = 0, kPackLo = 1, kPackLoTrue = 2, kPackHiSmall = 3 };
+__host__ __device__ inline __half pack_half(float v, int kind) {
+  const __half hi = __float2half_rn(v);
+  const float hf = __half2float(hi);
+  if (kind == kPackLo) return __float2half_rn((v - hf) * kLoScale);
+  if (kind == kPackLoTrue) return __float2half_rn(v - hf);
+  if (kind == kPackHiSmall) return __float2half_rn(hf * kLoInvScale);
+  return hi;
+}
 struct PackWrite {
   const float* w;
   uint8_t* img;
-  void operator()(size_t byte, int src, bool lo) const {
-    const float v = w[src];
-    const __half hi = __float2half_rn(v);
-    *reinterpret_cast<__half*>(img + byte) = lo ? __float2half_rn((v - __half2float(hi)) * kLoScale) : hi;
+  void operator()(size_t byte, int src, int kind) const {
+    *reinterpret_cast<__half*>(img + byte) = pack_half(w[src], kind);
   }
 };
 struct PackMap {
   int32_t* map;
-  void operator()(size_t byte, int src, bool lo) const { map[byte >> 1] = src * 2 + (lo ? 1 : 0); }
+  void operator()(size_t byte, int src, int kind) const { map[byte >> 1] = src * 4 + kind; }
 };
 
 }  // namespace deqsci

@@ -1,16 +1,19 @@
-// Kernel group 2d: the FIRST conv layer of the denoiser on tensor cores (split-fp16 precision).
+// Kernel group 2d: the FIRST conv layer of the denoiser on tensor cores (split-fp16 precision, K-packed).
 //
-// Input: the 8-channel planes written by gap_prep_kernel (gap.cu): channels-last [frames,Hc,Wc,8],
-// FFDNet = {sigma, 4 unshuffled sub-pixels, 0 x 3}, DnCNN = {pixel, 0 x 7}; the TMA box asks for 16 channels
-// and the missing 8 arrive as zeros (out-of-bounds fill).  K per tap is thus padded to one UMMA_K (16), so a tile costs 9 taps x (N=128 + N=64) = 864 MMA cycles instead of the 2880 FMA
-// cycles per pixel-row the CUDA-core kernel needs, and the K = 45 / 9 gather disappears: a tap is a
-// UMMA descriptor 32 bytes (one pixel) further into a TMA-loaded input row (32-byte swizzle).
+// The layer has C = 5 (FFDNet: sigma + 4 unshuffled sub-pixels) or 1 (DnCNN) input channels, so one UMMA_K = 16
+// row per pixel has room for all three products of the precision split at once:
+//     A row (gap_prep, gap.cu)  = [ Ah x C | Ah x C | Al' x C | 0 ]           Al' = (a - Ah) * 2^11
+//     B row (tcf_layout below)  = [ Wh x C | Wl x C | Wh * 2^-11 x C | 0 ]    Wl = w - Wh at its TRUE scale
+//     A . B = Ah.Wh + Ah.Wl + Al.Wh                                           (fp32 accumulation in TMEM)
+// -- ONE MMA per tap into 64 accumulator columns (two MMAs into 128 columns with separate hi / lo planes before).
+// Wl and Wh * 2^-11 sit in fp16's subnormal range, which still carries the 6-10 bits the correction terms need
+// (CPU emulation: tests/tools/emulate_precision.py first_kpack; the per-iterate error is unchanged).
+// A tap is a UMMA descriptor 32 bytes (one pixel) further into a TMA-loaded input row (32-byte swizzle).
 //
-// Structure = the rolling-row pipeline of conv_tc.cu (LD_ROLL) with the epilogue of conv_tc2.cu:
-// two CTAs per SM (110 KB, 96 registers, 256 TMEM columns each) hide each other's epilogue latency;
-// warp 0 TMA producer (4-slot ring of input rows with 1-pixel halo, hi + lo planes), warp 1 TMEM
-// allocator + MMA issuer, warps 2-9 epilogue (tcgen05.ld -> affine + ReLU -> hi/lo split -> swizzled
-// smem -> TMA store of 32 pixels x 32 channels per warp and plane).
+// Structure = the rolling-row pipeline of conv_tc.cu (LD_ROLL) with the epilogue of conv_tc2.cu; two CTAs per SM
+// (84 KB, 96 registers, 256 TMEM columns = 4 accumulator buffers each) hide each other's epilogue latency;
+// warp 0 TMA producer (6-slot ring of input rows with 1-pixel halo), warp 1 TMEM allocator + MMA issuer,
+// warps 2-9 epilogue (tcgen05.ld -> affine + ReLU -> hi/lo split -> swizzled smem -> TMA store of whole pixels).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,16 +27,16 @@ using namespace ptx;
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 320;
-constexpr int kSlots = 4;
-constexpr int kRowBytes = 32;                                  // 16 channels fp16
-constexpr int kPlaneBytes = 5 * 1024;                          // 130 pixels x 32 B = 4160 B, padded
-constexpr int kSlotBytes = 2 * kPlaneBytes;
-constexpr int kTxBytes = 2 * (kTileM + 2) * kRowBytes;
-constexpr int kTapBytesB = 128 * kRowBytes;                    // [Wh | Wl'] rows x 16 k
-constexpr int kWBytes = 9 * kTapBytesB;                        // 36 KB
+constexpr int kSlots = 6;
+constexpr int kRowBytes = 32;                                  // one K = 16 row, fp16
+constexpr int kSlotBytes = 5 * 1024;                           // 130 pixels x 32 B = 4160 B, padded
+constexpr int kTxBytes = (kTileM + 2) * kRowBytes;
+constexpr int kTapBytesB = 64 * kRowBytes;                     // 64 cout rows x 16 k
+constexpr int kWBytes = 9 * kTapBytesB;                        // 18 KB
 constexpr int kStageBytes = 4096;                              // one staging tile: 32 px x 64 ch fp16 (per warp pair: hi tile, lo tile)
-constexpr int kAccCols = 128;
-constexpr int kTmemCols = 256;
+constexpr int kAccCols = 64;
+constexpr int kBufs = 4;                                       // accumulator buffers
+constexpr int kTmemCols = kBufs * kAccCols;                    // 256
 constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
 
 struct Params {
@@ -63,7 +66,7 @@ __device__ __forceinline__ Item decode(const Params& p, long long item) {
 // epilogue skips the per-channel multiply-add and its shared-memory loads
 template <bool AFFINE>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_map,
                      const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
                      const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +75,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
   uint8_t* a_s = w_s + kWBytes;
   uint8_t* st_s = a_s + kSlots * kSlotBytes;
   uint8_t* tail = st_s + 8 * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0] w, full[S], empty[S], tfull[2], tempty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0] w, full[S], empty[S], tfull[kBufs], tempty[kBufs]
   float* aff_s = reinterpret_cast<float*>(tail + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
   pdl_launch_dependents();       // the next kernel's prologue may overlap this grid's tail (see conv_tc2.cu)
@@ -81,12 +84,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
   auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
   auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlots + s]); };
   auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlots + b]); };
-  auto bar_tempty = [&](int b) { return smem_u32(&bars[3 + 2 * kSlots + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[1 + 2 * kSlots + kBufs + b]); };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 8); }
+    for (int b = 0; b < kBufs; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 8); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -114,16 +117,14 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
           mbar_wait(bar_empty(slot), phase ^ 1);
           mbar_arrive_expect_tx(bar_full(slot), kTxBytes);
           const uint32_t dst = smem_u32(a_s + slot * kSlotBytes);
-          tma_load_4d(dst, &in_hi, bar_full(slot), 0, it.w0 - 1, it.h0 - 1 + q, it.nf);
-          tma_load_4d(dst + kPlaneBytes, &in_lo, bar_full(slot), 0, it.w0 - 1, it.h0 - 1 + q, it.nf);
+          tma_load_4d(dst, &in_map, bar_full(slot), 0, it.w0 - 1, it.h0 - 1 + q, it.nf);
           if (++slot == kSlots) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {
-      constexpr uint32_t idesc_main = make_idesc(kTileM, 128);
-      constexpr uint32_t idesc_lo = make_idesc(kTileM, 64);
+      constexpr uint32_t idesc = make_idesc(kTileM, 64);
       mbar_wait(bar_w, 0);
       const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
       int first = 0;
@@ -151,9 +152,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               const int tap = ky * 3 + kx;
-              const uint64_t b_w = sdesc_sw32(w_base + tap * kTapBytesB);
-              umma_f16(d_main, sdesc_sw32(a_row + kx * kRowBytes), b_w, idesc_main, tap != 0);
-              umma_f16(d_main + 64, sdesc_sw32(a_row + kPlaneBytes + kx * kRowBytes), b_w, idesc_lo, 1u);
+              umma_f16(d_main, sdesc_sw32(a_row + kx * kRowBytes), sdesc_sw32(w_base + tap * kTapBytesB), idesc,
+                       tap != 0);
             }
           }
           const int dead = (first + j) % kSlots;
@@ -163,7 +163,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
             umma_commit(bar_empty((dead + 2) % kSlots));
           }
           umma_commit(bar_tfull(buf));
-          if (++buf == 2) { buf = 0; tphase ^= 1; }
+          if (++buf == kBufs) { buf = 0; tphase ^= 1; }
         }
         first = wait_slot;
         first_phase = wait_phase;
@@ -190,9 +190,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
         uint32_t hi_pk[16], lo_pk[16];
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-          uint32_t acc[16], cor[16];
+          uint32_t acc[16];
           tmem_ld16(t_row + half * 32 + part * 16, acc);
-          tmem_ld16(t_row + 64 + half * 32 + part * 16, cor);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -204,7 +203,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              float a = fmaf(__uint_as_float(cor[i + u]), kLoInvScale, __uint_as_float(acc[i + u]));
+              float a = __uint_as_float(acc[i + u]);
               if (AFFINE) a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
               v[u] = p.relu ? fmaxf(a, 0.f) : a;
             }
@@ -241,7 +240,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
             bulk_commit();
           }
         }
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
+        if (++buf == kBufs) { buf = 0; tphase ^= 1; }
       }
     }
     bulk_wait0();
@@ -255,20 +254,20 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_con
 
 size_t tcf_weight_image_bytes() { return tcf::kWBytes; }
 
-// w [64 cout][cin][3][3] fp32 (cin = 5 or 1) -> [tap][128 rows: hi(W) | lo'(W)][16 k] fp16, 32-byte swizzle
-// (16-byte chunk index XOR bit 2 of the row index); k >= cin is zero.
+// w [64 cout][cin][3][3] fp32 (cin = 5 or 1, 3 * cin <= 16) -> [tap][64 cout rows][16 k] fp16, 32-byte swizzle
+// (16-byte chunk index XOR bit 2 of the row index); unused k slots are zero.
 template <class Emit>
 static void tcf_layout(int cin, Emit emit) {
   for (int tap = 0; tap < 9; ++tap) {
     const int ky = tap / 3, kx = tap % 3;
-    for (int n = 0; n < 128; ++n) {
-      const int co = n & 63;
-      for (int k = 0; k < cin; ++k) {
-        const size_t byte = (size_t)tap * tcf::kTapBytesB + (size_t)n * 32 + (size_t)(((k >> 3) ^ ((n >> 2) & 1)) << 4) +
-                            (size_t)(k & 7) * 2;
-        emit(byte, ((co * cin + k) * 3 + ky) * 3 + kx, n >= 64);
+    for (int n = 0; n < 64; ++n)
+      for (int kk = 0; kk < 3 * cin; ++kk) {        // K slots: [Wh x cin | Wl (true scale) x cin | Wh * 2^-11 x cin]
+        const int k = kk % cin;
+        const int kind = kk < cin ? kPackHi : (kk < 2 * cin ? kPackLoTrue : kPackHiSmall);
+        const size_t byte = (size_t)tap * tcf::kTapBytesB + (size_t)n * 32 + (size_t)(((kk >> 3) ^ ((n >> 2) & 1)) << 4) +
+                            (size_t)(kk & 7) * 2;
+        emit(byte, ((n * cin + k) * 3 + ky) * 3 + kx, kind);
       }
-    }
   }
 }
 void tcf_pack_weights(const float* w, int cin, uint8_t* img) {
@@ -282,7 +281,7 @@ bool tcf_supported(int Wc) {
   return enabled && Wc > 64;
 }
 
-// planes_in: [2][NF,Hc,Wc,8] fp16 (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
+// planes_in: [NF,Hc,Wc,16] fp16, K-packed rows (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
                          int Wc, cudaStream_t st) {
@@ -294,10 +293,10 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   p.strip_rows = R;
   p.strips_y = (Hc + R - 1) / R;
   p.n_items = (long long)NF * p.tiles_x * p.strips_y;
-  CUtensorMap in_hi, in_lo, out_hi, out_lo;
+  CUtensorMap in_map, out_hi, out_lo;
   int rc;
-  if ((rc = make_plane_map(&in_hi, planes_in, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
-  if ((rc = make_plane_map(&in_lo, planes_in + in_plane_elems, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
+  (void)in_plane_elems;
+  if ((rc = make_plane_map(&in_map, planes_in, kPrepChannels, NF, Hc, Wc, 16, tcf::kTileM + 2, 1, 32))) return rc;
   if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 64, 32, 1, 128))) return rc;
   const int grid = (int)(p.n_items < 2 * num_sms() ? p.n_items : 2 * num_sms());      // two CTAs per SM
@@ -305,13 +304,13 @@ int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __ha
   if (scale || bias) {
     DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tcf::kSmemBytes));
-    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<true>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi,
-                           in_lo, out_hi, out_lo, p));
+    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<true>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_map,
+                           out_hi, out_lo, p));
   } else {
     DEQSCI_CUDA(cudaFuncSetAttribute(tcf::conv_first_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tcf::kSmemBytes));
-    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<false>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_hi,
-                           in_lo, out_hi, out_lo, p));
+    DEQSCI_CUDA(launch_pdl(tcf::conv_first_tc_kernel<false>, (unsigned)grid, tcf::kThreads, tcf::kSmemBytes, st, in_map,
+                           out_hi, out_lo, p));
   }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;

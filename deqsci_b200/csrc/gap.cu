@@ -180,7 +180,7 @@ extern "C" int deqsci_gap_vjp(const float* v, const float* phi, const float* phi
 
 // ------------------------------------------------------------------------------------------------
 // Prologue of the tensor-core first conv layer: (optional) GAP step, then the frame-major,
-// channels-last 8-channel input planes that conv_tc_first.cu loads with TMA (as 16: out-of-bounds fill).
+// channels-last K-packed input plane that conv_tc_first.cu loads with TMA.
 //   FFDNet: one thread per half-resolution pixel (b,i,j): z' of its 2x2 fine pixels for all T frames,
 //           plane row [b*T+t, i, j, :] = {sigma, z'(0,0), z'(0,1), z'(1,0), z'(1,1), 0 x 11}
 //           (pixel-unshuffle + noise map of networks/ffdnet/functions.py:16-53; because sigma is a real
@@ -242,9 +242,16 @@ __global__ void __launch_bounds__(128) gap_prep_kernel(const float* __restrict__
         const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
         split_f16(v, hi[c], lo[c]);
       }
+      // one K = 16 row per pixel: [hi x C | hi x C | lo' x C | 0], C = 5 (FFDNet) or 1 (DnCNN) -- see conv_tc_first.cu
+      constexpr int C = (KIND == DEQSCI_NET_FFDNET) ? 5 : 1;
+      __align__(16) __half krow[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) krow[c] = __float2half_rn(0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { krow[c] = hi[c]; krow[C + c] = hi[c]; krow[2 * C + c] = lo[c]; }
       const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * kPrepChannels;
-      *reinterpret_cast<uint4*>(planes + row) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(planes + plane_elems + row) = *reinterpret_cast<const uint4*>(lo);
+      reinterpret_cast<uint4*>(planes + row)[0] = reinterpret_cast<const uint4*>(krow)[0];
+      reinterpret_cast<uint4*>(planes + row)[1] = reinterpret_cast<const uint4*>(krow)[1];
     }
   }
 }
@@ -327,15 +334,21 @@ __global__ void __launch_bounds__(128) gap_prep_t8_kernel(const float* __restric
         const int c = (KIND == DEQSCI_NET_FFDNET) ? 1 + s : 0;
         split_f16(zv[s][t], hi[c], lo[c]);
       }
+      // one K = 16 row per pixel: [hi x C | hi x C | lo' x C | 0], C = 5 (FFDNet) or 1 (DnCNN) -- see conv_tc_first.cu
+      constexpr int C = (KIND == DEQSCI_NET_FFDNET) ? 5 : 1;
+      __align__(16) __half krow[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) krow[c] = __float2half_rn(0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { krow[c] = hi[c]; krow[C + c] = hi[c]; krow[2 * C + c] = lo[c]; }
       const long long row = ((((long long)b * T + t) * Hc + i) * Wc + j) * kPrepChannels;
-      *reinterpret_cast<uint4*>(planes + row) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(planes + plane_elems + row) = *reinterpret_cast<const uint4*>(lo);
+      reinterpret_cast<uint4*>(planes + row)[0] = reinterpret_cast<const uint4*>(krow)[0];
+      reinterpret_cast<uint4*>(planes + row)[1] = reinterpret_cast<const uint4*>(krow)[1];
     }
   }
 }
 
-// planes: [2][B*T, Hc, Wc, 8] fp16 (kPrepChannels; the first layer's TMA box asks for 16 channels and gets zeros for
-// the missing 8: out-of-bounds fill); plane_elems = B*T*Hc*Wc*8.  y/phi/phi_sum/zprime_out may be null
+// planes: [B*T, Hc, Wc, 16] fp16 (kPrepChannels): one K-packed row per pixel; plane_elems = B*T*Hc*Wc*16.  y/phi/phi_sum/zprime_out may be null
 // when do_gap == 0 (the planes are then built from z itself).
 int gap_prep_launch(int kind, const float* z, const float* y, const float* phi, const float* phi_sum,
                     float* zprime_out, __half* planes, long long plane_elems, float sigma, int B, int H, int W,
