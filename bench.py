@@ -46,13 +46,51 @@ HIDDEN_FLOP_PER_LAUNCH_PER_MEAS = 2 * 9 * 64 * 64 * (H // 2) * (W // 2) * T
 STACK_FLOP_PER_F_PER_MEAS = 2 * 9 * (5 * 64 + 13 * 64 * 64 + 64 * 4) * (H // 2) * (W // 2) * T
 
 
-def synthetic_batch(start, count):
+def _smooth(g, size, cells):
+    """Low-pass random image in [0,1]: U[0,1) noise on a cells x cells grid, bicubic-upsampled."""
+    import torch.nn.functional as F
+    c = torch.rand(1, 1, cells, cells, generator=g)
+    return F.interpolate(c, size=(size, size), mode="bicubic", align_corners=False)[0, 0]
+
+
+def synthetic_cube(g, kind):
+    """One ground-truth cube [H,W,T] in [0,1] from generator g.
+    uniform: x ~ U[0,1) per voxel (white noise; SURVEY 8(d) default).
+    lowpass: every frame an independent low-pass image.
+    video:   one low-pass scene (three octaves) translated by a whole-pixel velocity per frame plus 1 % sensor
+             noise -- temporally coherent like the benchmark videos ('optionally low-pass
+             filtered to be video-like; state which')."""
+    if kind == "uniform":
+        return torch.rand(H, W, T, generator=g)
+    if kind == "lowpass":
+        fr = [0.7 * _smooth(g, H, 10) + 0.3 * _smooth(g, H, 40) for _ in range(T)]
+        x = torch.stack(fr, 2)
+    elif kind == "video":
+        P = 2 * 2 * (T - 1)                               # margin for |v| <= 2 pixels per frame
+        S = H + P
+        base = 0.6 * _smooth(g, S, 10) + 0.3 * _smooth(g, S, 36) + 0.1 * _smooth(g, S, 120)
+        v = torch.randint(-2, 3, (2,), generator=g)
+        o = P // 2
+        fr = [base[o + int(v[0]) * t:o + int(v[0]) * t + H, o + int(v[1]) * t:o + int(v[1]) * t + W] for t in range(T)]
+        x = torch.stack(fr, 2) + 0.01 * torch.randn(H, W, T, generator=g)
+    else:
+        raise ValueError(kind)
+    x = x - x.min()
+    return (x / x.max().clamp_min(1e-6)).contiguous()
+
+
+DATA_KIND = os.environ.get("DEQSCI_BENCH_DATA", "video")
+
+
+def synthetic_batch(start, count, kind=None):
     """Measurement i is drawn from torch.Generator().manual_seed(SEED + i): identical under any
-    sharding.  x ~ U[0,1), Phi ~ Bernoulli(0.5), y = sum_t Phi*x."""
+    sharding.  x per `kind` (synthetic_cube), Phi ~ Bernoulli(0.5) independent per measurement,
+    y = sum_t Phi*x."""
+    kind = kind or DATA_KIND
     ys, ps, xs = [], [], []
     for i in range(start, start + count):
         g = torch.Generator().manual_seed(SEED + i)
-        x = torch.rand(H, W, T, generator=g)
+        x = synthetic_cube(g, kind)
         phi = (torch.rand(H, W, T, generator=g) < 0.5).float()
         xs.append(x)
         ps.append(phi)

@@ -21,6 +21,19 @@ def default_precision():
     return name
 
 
+def graph_needed(module, *tensors):
+    """True when an autograd graph built by this call could be back-propagated through: grad mode on and a
+    parameter of `module` or one of `tensors` requires grad.  The native kernels return graph-less results,
+    so they serve a call only when this is False (eval mode alone does not make a call inference: the
+    reference builds the graph and registers its implicit-differentiation hook in eval mode too, eval only
+    freezes the BatchNorm statistics)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return True
+    return module is not None and any(p.requires_grad for p in module.parameters())
+
+
 def _f32(a):
     if isinstance(a, torch.Tensor):
         a = a.detach().cpu().numpy()

@@ -148,7 +148,9 @@ class FFDNet(nn.Module, NativePlanCache):
     def uses_native(self, x):
         # train mode means batch-statistics BatchNorm (and running-stat updates) on every call, which
         # the folded-BN plan does not express: the native path is the eval-mode network.
-        return x.is_cuda and self.num_input_channels == 1 and not self.training
+        # (the input is detached before the network, models.py:103-104: only the parameters can need a graph)
+        from ...native import graph_needed
+        return x.is_cuda and self.num_input_channels == 1 and not self.training and not graph_needed(self)
 
     def forward(self, x, noise_sigma):
         if self.uses_native(x):

@@ -71,6 +71,9 @@ class DnCNN(nn.Module, NativePlanCache):
         # statistics and the spectral-norm power iteration are per-call state the plan does not express)
         if not (x.is_cuda and self.channels == 1):
             return False
+        from ....native import graph_needed
+        if graph_needed(self, x):
+            return False
         return (not self.training) or (not torch.is_grad_enabled() and self._stateless_in_train_mode())
 
     def forward(self, x):

@@ -8,6 +8,8 @@ At inference the whole map is ONE C-ABI call (deqsci_iterate): the GAP step is f
 conv kernel, the residual subtract and layout change into the last.  The sigma schedule of the
 'ffdnet' tag (reset to 60/255 when y.mean() changes, else x0.971 per call, :409-413) is kept on
 the host as an fp32 scalar, without the reference's per-call device sync."""
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -30,7 +32,8 @@ class EquilibriumProxGradSCI(nn.Module):
         self.eta = eta
         self.y = 0                    # mean of the measurement the sigma schedule belongs to
         self._n = 0                   # calls made since the last reset: the next call uses sigma_table[_n]
-        self._y_key = None
+        self._y_ref = None            # weak reference to the measurement tensor whose mean is self.y ...
+        self._y_version = None        # ... and its version counter when the mean was taken
         self._undo = None
         self.n_sigma_frames = 8
 
@@ -55,24 +58,37 @@ class EquilibriumProxGradSCI(nn.Module):
         return torch.full((self.n_sigma_frames,), float(self._sigma), dtype=torch.float32, device=dev)
 
     def _observe(self, y):
-        """Reference :409-412: `if self.y != y.mean(): reset`.  The mean of a tensor we have already seen
-        (same storage, same version) is not recomputed, so a solver loop costs one device sync per new
-        measurement instead of one per call.  Returns True when the schedule was reset."""
-        key = (y.data_ptr(), y._version, tuple(y.shape), str(y.device))
-        if key != self._y_key:
-            mean = float(y.mean())
-            self._y_key = key
-            if self.y != mean:
-                self.y = mean
-                self._n = 0
-                return True
+        """Reference :409-412: `if self.y != y.mean(): reset` — the measurement means are compared BY VALUE.
+        The mean is recomputed for every tensor object not seen before; only the very same live tensor
+        object with an unchanged version counter (what a solver loop passes on every call of one solve)
+        skips the reduction, so a solve costs one device sync instead of one per call.  Identity is held by
+        a weak reference, never by address: a new measurement allocated where a freed one lived is a new
+        object and is measured again.  Returns True when the schedule was reset."""
+        try:
+            version = y._version
+        except RuntimeError:          # inference tensors carry no version counter: always re-measure
+            version = None
+        seen = self._y_ref() if self._y_ref is not None else None
+        if seen is y and version is not None and version == self._y_version:
+            return False
+        mean = float(y.mean())
+        self._y_ref, self._y_version = weakref.ref(y), version
+        if self.y != mean:
+            self.y = mean
+            self._n = 0
+            return True
         return False
+
+    def __getstate__(self):
+        state = self.__dict__.copy()  # weak references do not pickle (torch.save of the whole module)
+        state["_y_ref"] = state["_y_version"] = state["_undo"] = None
+        return state
 
     def _advance_sigma(self, y):
         """sigma of this call: 60/255 right after a reset, else the previous one times 0.971 (:413).
         (The very first call of a measurement whose mean equals the stored one decays, as in the
         reference.)"""
-        self._undo = (self.y, self._n, self._y_key)          # state before this call (rollback_call)
+        self._undo = (self.y, self._n, self._y_ref, self._y_version)      # state before this call (rollback_call)
         if self._observe(y):
             self._n = 1
             return self.sigma_at(0)
@@ -86,7 +102,7 @@ class EquilibriumProxGradSCI(nn.Module):
         speculative iteration past convergence calls this; the map has no other per-call state in
         eval mode)."""
         if self.nonlinear_op.tag == 'ffdnet' and self._undo is not None:
-            self.y, self._n, self._y_key = self._undo
+            self.y, self._n, self._y_ref, self._y_version = self._undo
             self._undo = None
 
     def skip_call(self):
@@ -134,14 +150,18 @@ class EquilibriumProxGradSCI(nn.Module):
     def _autograd_forward(self, z, y, Phi, Phi_sum):
         """Graph-attached evaluation for training (PyTorch autograd; not the inference hot path).
         cuDNN's TF32 convolutions (PyTorch's default on Ampere+) put 1e-3..1e-2 errors on the
-        iterates and gradients, far outside the parity bar, so the library path is pinned to fp32."""
-        if z.is_cuda and torch.backends.cudnn.allow_tf32:
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
+        iterates and gradients, far outside the parity bar, so the library path is pinned to fp32 — for the
+        process, because the backward kernels of this graph run later, outside any scope this call could
+        open (`restore_library_math()` undoes it)."""
+        if z.is_cuda:
+            pin_fp32_library_math()
         bsz, w, h, c = z.shape
         tag = self.nonlinear_op.tag
-        fb = torch.sum(z * Phi, dim=3)
-        z = z + ((y - fb) / Phi_sum)[:, :, :, None] * Phi
+        if self.A is cg_utils.A_torch_ and self.At is cg_utils.At_torch_:
+            fb = torch.sum(z * Phi, dim=3)
+            z = z + ((y - fb) / Phi_sum)[:, :, :, None] * Phi
+        else:                         # user-supplied operator callables: the same ones the eval path uses
+            z = z + self.At((y - self.A(z, Phi)) / Phi_sum, Phi)
         frames = z.permute(0, 3, 1, 2).contiguous().view(bsz * c, 1, w, h)
         if tag == 'ffdnet':
             self.n_sigma_frames = bsz * c
@@ -154,3 +174,24 @@ class EquilibriumProxGradSCI(nn.Module):
         if tag == 'conv2d':
             return self.nonlinear_op(frames).view(bsz, c, w, h).permute(0, 2, 3, 1)
         raise DeqsciError("nonlinear_op tag %r is not on the DE-GAP path built here" % (tag,))
+
+
+_tf32_before = None
+
+
+def pin_fp32_library_math():
+    """fp32 (not TF32) cuDNN / cuBLAS math for the autograd-attached part of the training step; remembers the
+    flags it found so restore_library_math() can put them back."""
+    global _tf32_before
+    if torch.backends.cudnn.allow_tf32 or torch.backends.cuda.matmul.allow_tf32:
+        if _tf32_before is None:
+            _tf32_before = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def restore_library_math():
+    global _tf32_before
+    if _tf32_before is not None:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = _tf32_before
+        _tf32_before = None

@@ -198,10 +198,11 @@ class _BoundIterate:
 
 class DEQFixedPoint(nn.Module):
     """DEQFixedPoint(f, solver, **kwargs).forward(x=y, Phi, Phi_sum, initial_point, train_flag)
-    (reference :241-281).  Inference (denoiser in eval mode or grad disabled): solver under
-    no_grad, one more f call = the reconstruction; the reference's second post-solver call only
-    feeds the backward hook, so it is skipped and just advances the sigma schedule.  Training:
-    graph-attached f call plus the implicit-differentiation backward hook, as in the reference."""
+    (reference :241-281).  Inference (grad mode off, or no parameter / input requires grad): solver
+    under no_grad, one more f call = the reconstruction; the reference's second post-solver call only
+    feeds the backward hook, so it is skipped and just advances the sigma schedule.  Otherwise (train OR
+    eval mode): graph-attached f call plus the implicit-differentiation backward hook, as in the
+    reference; in eval mode the no_grad solve still runs on the folded-BatchNorm native plan."""
 
     def __init__(self, f, solver, **kwargs):
         super().__init__()
@@ -211,9 +212,16 @@ class DEQFixedPoint(nn.Module):
         self.forward_res = None
         self.backward_res = None
 
-    def _inference(self):
-        op = getattr(self.f, "nonlinear_op", None)
-        return (not torch.is_grad_enabled()) or (op is not None and not op.training)
+    def _inference(self, *tensors):
+        """No graph can be asked for: grad mode off, or nothing that requires grad takes part.  Eval mode
+        alone is NOT inference (reference :268-280 builds the graph-attached call and the hook whenever it
+        runs; eval only freezes the BatchNorm statistics)."""
+        if not torch.is_grad_enabled():
+            return True
+        if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+            return False
+        params = getattr(self.f, "parameters", None)
+        return params is not None and not any(p.requires_grad for p in params())
 
     # ---- device-resident driver: the whole solve (+ the final f call at inference) as one C-ABI call ---
     def _driver_mode(self, z):
@@ -262,7 +270,10 @@ class DEQFixedPoint(nn.Module):
         init_point = torch.zeros_like(Phi.expand(x.shape[0], *Phi.shape[1:])) if initial_point is None else initial_point
         bound = _BoundIterate(self.f, x, Phi, Phi_sum)
         mode = self._driver_mode(init_point)
-        inference = self._inference()
+        # train_flag=False is the caller's declaration that no backward will follow (the reference's own test
+        # loop passes it, :176 of training/sci_equilibrium_training.py; its hook registration on that flag is
+        # commented out at :279-280) -> inference path even with grad mode on
+        inference = (not train_flag) or self._inference(x, Phi, Phi_sum, init_point)
         if inference and mode == "eval":
             return self._forward_driver(x, Phi, Phi_sum, init_point, True, mode)
         if mode is not None:           # the no_grad solve on the driver; the post-solver calls follow below

@@ -455,6 +455,57 @@ def test_full_scene_psnr_vs_reference(dev, full_recon, d, scene):
     assert rel_l2(crop, full_recon[key + "_z_crop"]) <= 1e-3
 
 
+def test_sigma_schedule_resets_for_function_scoped_measurements(dev, full_recon):
+    """drop8 then runner8, each measurement a function-scoped tensor (the caching allocator
+    hands the second one the address the first just freed).  The schedule must reset by VALUE (reference
+    solvers/equilibrium_solvers_yaping.py:409-413) -- both reconstructions match the reference's; with the
+    old address-keyed cache the second one started at sigma_182 ~ 1e-3 instead of 60/255."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    solver = build_solver("ffdnet", dev)
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=180, tol=1e-5)
+    ptrs = []
+
+    def one(scene):
+        gt, mask, meas = load_scene(scene)
+        Phi = t(mask[None], dev)
+        y = t(meas[None, :, :, 0], dev)                      # dies at return
+        ptrs.append(y.data_ptr())
+        z = deq.forward(y, Phi, Phi_sum_(Phi), initial_point=At_torch_(y, Phi), train_flag=False)
+        return orc.psnr(gt[None, :, :, 0:8], z.clip(0, 1).cpu().numpy()), z[0, 96:160, 96:160].cpu().numpy()
+
+    for scene in ("drop8", "runner8"):
+        key = "ffdnet_%s_0" % scene
+        psnr, crop = one(scene)
+        assert solver._n == 182                              # 180 solver calls + 2 post-solver calls since the reset
+        assert abs(psnr - float(full_recon[key + "_psnr"])) <= 0.05, (scene, psnr, float(full_recon[key + "_psnr"]))
+        if scene == "drop8":
+            assert rel_l2(crop, full_recon[key + "_z_crop"]) <= 1e-3
+    assert ptrs[0] == ptrs[1], "the allocator did not reuse the address: the regression scenario was not exercised"
+
+
+def test_eval_mode_with_grad_builds_the_graph(dev, small_vectors):
+    """eval mode + grad enabled + trainable parameters is a differentiable call (reference
+    solvers/new_equilibrium_utils_yaping.py:268-280 attaches the graph and the hook regardless of mode);
+    train_flag=False or no_grad is inference and gives the same reconstruction."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    Phi, y = t(v["crop_Phi"], dev), t(v["crop_y"], dev)
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    solver = build_solver("SimpleCNN", dev)
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=12, tol=1e-5)
+    z_inf = deq.forward(y, Phi, Ps, initial_point=x0, train_flag=False)
+    assert not z_inf.requires_grad
+    z = deq.forward(y, Phi, Ps, initial_point=x0)            # eval mode, grad on, default train_flag
+    assert z.requires_grad
+    assert rel_l2(z.detach().cpu().numpy(), z_inf.cpu().numpy()) <= 1e-4
+    z.square().mean().backward()
+    g = [p.grad for p in solver.parameters()]
+    assert all(gi is not None and torch.isfinite(gi).all() for gi in g) and any(float(gi.abs().max()) > 0 for gi in g)
+    assert deq.backward_res is not None
+
+
 # ---------------------------------------------------------------------------------------------
 # (6) the caller: test_solver_sci over all benchmark scenes present (configs 2 and 3)
 # ---------------------------------------------------------------------------------------------
