@@ -24,7 +24,7 @@ class SolverOpts(Structure):
 
 class SolverResult(Structure):
     _fields_ = [("residual", ctypes.c_double), ("iterations", c_int), ("f_calls", c_int), ("converged", c_int),
-                ("sigma_next", c_float)]
+                ("sigma_next", c_float), ("min_sample_residual", ctypes.c_double)]
 
 
 class BNParams(Structure):
@@ -68,6 +68,14 @@ SIGNATURES = {
     "deqsci_adjoint_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "deqsci_adjoint_solve": (c_int, [_P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
                                      c_int, c_int, c_int, c_int, _P]),
+    "deqsci_comm_bytes": (c_size_t, [c_longlong]),
+    "deqsci_comm_alloc": (c_int, [c_longlong, POINTER(_P), _P]),
+    "deqsci_comm_open": (c_int, [_P, POINTER(_P)]),
+    "deqsci_comm_close": (c_int, [_P]),
+    "deqsci_comm_free": (c_int, [_P]),
+    "deqsci_comm_error": (c_int, [_P, c_longlong, POINTER(c_int)]),
+    "deqsci_adam_allreduce_step": (c_int, [_P, _P, _P, POINTER(_P), c_int, c_int, c_longlong, c_float, c_float, c_float,
+                                           c_float, c_int, c_float, ctypes.c_uint, _P]),
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_pair_strip_rows": (c_int, [c_int, c_int, c_int, c_int]),

@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(1024) anderson_solve_kernel(const float* __res
   pdl_launch_dependents();
   pdl_wait_predecessor();
   __shared__ double s_g2[32], s_f2[32];
+  __shared__ float s_min[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double g2 = 0.0, f2 = 0.0;   // per-warp running sums over its samples (fixed order)
+  float rmin = 3.0e38f;        // smallest PER-SAMPLE residual among this warp's samples
   for (int b = warp; b < B; b += nwarps) {
     double acc[kMaxM + 1];
 #pragma unroll
@@ -217,19 +219,22 @@ __global__ void __launch_bounds__(1024) anderson_solve_kernel(const float* __res
       }
       g2 += acc[slot < kMaxM ? slot : 0];
       f2 += acc[kMaxM];
+      // what the reference's whole-batch test (:184) computes when this sample is solved on its own (batch 1)
+      rmin = fminf(rmin, (float)(sqrt(acc[slot < kMaxM ? slot : 0]) / ((double)res_eps + sqrt(acc[kMaxM]))));
       if (do_solve) bordered_solve(gb, m, n, lam, alpha + (long long)b * m);
     }
   }
-  if (lane == 0) { s_g2[warp] = g2; s_f2[warp] = f2; }
+  if (lane == 0) { s_g2[warp] = g2; s_f2[warp] = f2; s_min[warp] = rmin; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0.0, c = 0.0;
-    for (int w = 0; w < nwarps; ++w) { a += s_g2[w]; c += s_f2[w]; }
+    float mn = 3.0e38f;
+    for (int w = 0; w < nwarps; ++w) { a += s_g2[w]; c += s_f2[w]; mn = fminf(mn, s_min[w]); }
     const float ng = (float)sqrt(a), nf = (float)sqrt(c);
     res[0] = (float)((double)ng / ((double)res_eps + (double)nf));
     res[1] = ng;
     res[2] = nf;
-    res[3] = 0.f;
+    res[3] = mn;      // min over samples of the per-sample residual
   }
 }
 

@@ -362,7 +362,7 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     if (h->precision == DEQSCI_PREC_FP32)
       rc = conv_mid_fp32_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
                                 g.Wc, st);
-    else if (bn && bn[i].gamma) {
+    else if (bn && bn[i].running_mean) {      // a BatchNorm follows this conv (gamma / beta are NULL for affine=False)
       // train mode: raw conv + per-channel statistics, then batch-statistics BatchNorm (+ ReLU) in place
       rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
                                    g.Wc, st, bn_stats);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include <algorithm>
 
 using namespace deqsci;
 
@@ -178,6 +179,7 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
   };
   int current_k = 0, stop_k = -1;
   rc = DEQSCI_OK;
+  double min_sample = 1e300;          // smallest per-sample residual seen on the counted iterations
   for (int k = 2; k < o->max_iter && rc == DEQSCI_OK; ++k) {
     current_k = k;
     const int n = k < m ? k : m, s = k % m;
@@ -193,6 +195,7 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
       rc = DEQSCI_ERR_CUDA;
       break;
     }
+    if (k > 2) min_sample = std::min(min_sample, (cudaEventSynchronize(ev[k - 1]), (double)res_host[4 * (k - 1) + 3]));
     if (k > 2 && res_of(k - 1) < (double)o->tol) {      // iteration k was speculative
       undo_call();
       if (bn) rc = bn_running_snapshot(bn, n_layers, bn_backup, 1, st);
@@ -201,7 +204,10 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
     }
   }
   double res = 0.0;
-  if (rc == DEQSCI_OK && current_k >= 2) res = res_of(current_k);
+  if (rc == DEQSCI_OK && current_k >= 2) {
+    res = res_of(current_k);
+    min_sample = std::min(min_sample, (double)res_host[4 * current_k + 3]);
+  }
   if (rc == DEQSCI_OK) {
     // z = f(z*): the reconstruction DEQFixedPoint.forward returns
     if (o->final_call) rc = f_call(Xs(current_k % m), out);
@@ -217,6 +223,7 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
   result->f_calls = calls;
   result->converged = stop_k >= 0 ? 1 : 0;
   result->sigma_next = sigma;
+  result->min_sample_residual = min_sample < 1e299 ? min_sample : res;
   (void)stop_k;
   return DEQSCI_OK;
 }

@@ -6,6 +6,8 @@ The torch layers below are parameter containers; at inference (eval mode or grad
 runs the hand-written CUDA conv stack of libdeqsci — pixel-unshuffle + noise map folded into the
 first conv, BatchNorm folded into a per-channel affine, pixel-shuffle folded into the last conv.
 The layer-by-layer torch evaluation is kept only for the graph-attached training call."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -143,6 +145,7 @@ class FFDNet(nn.Module, NativePlanCache):
         H, W = int(z.shape[1]), int(z.shape[2])
         return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.num_input_channels == 1
                 and (getattr(self, "precision", None) or default_precision()) == "tc_split"
+                and os.environ.get("DEQSCI_TC_PAIR", "1") != "0"      # the train path lives in the CTA-pair kernel
                 and H % 2 == 0 and W % 2 == 0 and W // 2 > 64)
 
     def uses_native(self, x):

@@ -2,6 +2,8 @@
 (`DnCNN(channels, num_of_layers, lip, no_bn, adaptive, tag)`), used by cnn.ckpt (lip=0, 4 layers,
 no BN) and rsn_cnn.ckpt (lip=1: spectrally normalised convs).  state_dict keys: `dncnn.N.weight`
 or `dncnn.N.{weight_orig,weight,weight_u}`.  At inference forward runs libdeqsci's conv stack."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -61,6 +63,7 @@ class DnCNN(nn.Module, NativePlanCache):
         return (z.is_cuda and self.training and not torch.is_grad_enabled() and self.channels == 1 and plain
                 and any(isinstance(m, nn.BatchNorm2d) for m in self.dncnn)
                 and (getattr(self, "precision", None) or default_precision()) == "tc_split"
+                and os.environ.get("DEQSCI_TC_PAIR", "1") != "0"      # the train path lives in the CTA-pair kernel
                 and W > 64)
 
     def _stateless_in_train_mode(self):

@@ -176,6 +176,45 @@ class EquilibriumProxGradSCI(nn.Module):
         raise DeqsciError("nonlinear_op tag %r is not on the DE-GAP path built here" % (tag,))
 
 
+class EquilibriumADMMSCI(nn.Module):
+    """ADMM iterate of the SCI path — drop-in for the reference's EquilibriumADMMSCI
+    (solvers/equilibrium_solvers_yaping.py:438-465):
+
+        s  = z + u
+        z' = s + At((y - A s) / (Phi_sum + 1e-8))      the GAP step on z+u (native kernel)
+        x  = D(z' - u)                                 the denoiser REPLACES its input (no residual subtract)
+        u' = u - (z' - x)                              returns (z', u')
+
+    As in the reference the denoiser is called with ONE argument and must carry a `conv3d` attribute
+    (False = a batch of independent frames [B*T,1,H,W]); FFDNet (two arguments) and a DnCNN without that
+    attribute fail here exactly as they do there."""
+
+    def __init__(self, A, At, nonlinear_operator, eta, minval=-1, maxval=1):
+        super().__init__()
+        self.A = A
+        self.At = At
+        self.nonlinear_op = nonlinear_operator
+        self.minval = minval
+        self.maxval = maxval
+
+    def forward(self, z, u, y, Phi, Phi_sum):
+        from .. import ops
+        bsz, w, h, c = z.shape
+        s = z + u
+        if (s.is_cuda and not torch.is_grad_enabled() and self.A is cg_utils.A_torch_
+                and self.At is cg_utils.At_torch_):
+            zn = ops.gap_step(s, y, Phi, Phi_sum + 1e-8)
+        else:
+            zn = s + self.At((y - self.A(s, Phi)) / (Phi_sum + 1e-8), Phi)
+        if not self.nonlinear_op.conv3d:
+            x = self.nonlinear_op((zn - u).permute(0, 3, 1, 2).contiguous().view(bsz * c, 1, w, h))
+            x = x.view(bsz, c, w, h).permute(0, 2, 3, 1)
+        else:
+            x = self.nonlinear_op((zn - u).permute(0, 3, 1, 2).unsqueeze(1).contiguous())
+            x = x.squeeze(1).permute(0, 2, 3, 1)
+        return zn, u - (zn - x)
+
+
 _tf32_before = None
 
 

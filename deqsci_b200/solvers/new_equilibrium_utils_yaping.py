@@ -18,6 +18,8 @@ from ..ops import _req, _stream
 from ..utils import cg_utils
 
 MAX_M = 8
+# statistics of the most recent _anderson_core run that its reference-shaped return value has no room for
+LAST_SOLVE = {"min_sample_residual": None, "iterations": None}
 
 
 def _call_f(f, x, out):
@@ -96,6 +98,11 @@ class _ResidualRing:
         self.events[k].synchronize()
         return float(self.host[k, 1]) / (eps + float(self.host[k, 2]))
 
+    def min_sample(self, k):
+        """Smallest per-sample residual of iteration k (what a batch-1 run of that sample would have tested)."""
+        self.events[k].synchronize()
+        return float(self.host[k, 3])
+
 
 def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
     x0 = _req(x0, "x0")
@@ -135,6 +142,8 @@ def _anderson_core(f, x0, m, lam, max_iter, tol, beta, eps, keep_res):
     last = stop_k if stop_k is not None else current_k
     res_list = [ring.get(k, eps) for k in range(2, last + 1)] if last >= 2 else []
     res = res_list[-1] if res_list else None
+    LAST_SOLVE["min_sample_residual"] = min([ring.min_sample(k) for k in range(2, last + 1)], default=None) if last >= 2 else None
+    LAST_SOLVE["iterations"] = last
     out = st.slot(st.X, current_k % m).clone()
     return out, (res_list if keep_res else res)
 
@@ -171,6 +180,55 @@ def forward_iteration(f, x0, max_iter=50, tol=1e-5):
         if res[-1] < tol:
             break
     return f0, res
+
+
+def admmexp(f, x0, m=5, lam=1e-4, max_iter=50, tol=1e-2, beta=1.0):
+    """Plain ADMM fixed-point iteration on the pair (X, U) (reference :396-411): returns (X, U, res) with
+    res = ||X+ - X|| / (1e-5 + ||X+||) of the last step; on convergence the PREVIOUS pair is returned, as in
+    the reference.  m, lam, beta are accepted and unused, as there."""
+    X, U = x0[0], x0[1]
+    res = None
+    dev = X.device
+    scratch = res_dev = res_host = None
+    for k in range(2, max_iter):
+        new_X, new_U = f(X, U)
+        if new_X.is_cuda:
+            a, b = _req(new_X, "f(X,U)[0]"), _req(X, "X")
+            if scratch is None:
+                scratch = torch.empty(lib().deqsci_anderson_scratch_floats(1, 1, a.numel()), dtype=torch.float32, device=dev)
+                res_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+                res_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            with torch.cuda.device(dev):
+                check(lib().deqsci_residual(a.data_ptr(), b.data_ptr(), res_dev.data_ptr(), scratch.data_ptr(),
+                                            a.numel(), 1e-5, _stream(a)), "deqsci_residual")
+            res_host.copy_(res_dev, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            res = float(res_host[1]) / (1e-5 + float(res_host[2]))
+        else:
+            raise DeqsciError("admmexp on %s: deqsci_b200 has no CPU path" % new_X.device)
+        if res < tol:
+            break
+        X, U = new_X, new_U
+    return X, U, res
+
+
+class DEQFixedPointADMM(nn.Module):
+    """DEQFixedPointADMM(f, solver1, solver2, **kwargs).forward(x, Phi, Phi_sum, initial_point=[z0,u0])
+    (reference :414-451): runs solver1 on the pair map and returns z; no implicit-differentiation hook
+    (commented out in the reference)."""
+
+    def __init__(self, f, solver1, solver2, **kwargs):
+        super().__init__()
+        self.f = f
+        self.solver1 = solver1
+        self.solver2 = solver2
+        self.kwargs = kwargs
+        self.forward_res = None
+
+    def forward(self, x, Phi, Phi_sum, initial_point=None, train_flag=True):
+        init_point = [torch.zeros_like(x), torch.zeros_like(x)] if initial_point is None else initial_point
+        z, u, self.forward_res = self.solver1(lambda z, u: self.f(z, u, x, Phi, Phi_sum), init_point, **self.kwargs)
+        return z
 
 
 def _train_mode_batchnorm(op):
@@ -211,6 +269,7 @@ class DEQFixedPoint(nn.Module):
         self.kwargs = kwargs
         self.forward_res = None
         self.backward_res = None
+        self.forward_min_sample_res = None   # smallest per-sample residual of the forward solve (batched callers)
 
     def _inference(self, *tensors):
         """No graph can be asked for: grad mode off, or nothing that requires grad takes part.  Eval mode
@@ -260,6 +319,7 @@ class DEQFixedPoint(nn.Module):
         z, r = plan.reconstruct(x, Phi, Phi_sum, x0=init_point, sigma_start_call=start, final_call=final_call,
                                 bn_modules=op.bn_slots() if mode == "train" else None, **kw)
         self.forward_res = float(r.residual)
+        self.forward_min_sample_res = float(r.min_sample_residual)
         if op.tag == 'ffdnet':
             # inference: + the reference's second post-solver call, which is skipped
             f._n = start + int(r.f_calls) + (1 if final_call else 0)
@@ -280,7 +340,9 @@ class DEQFixedPoint(nn.Module):
             z = self._forward_driver(x, Phi, Phi_sum, init_point, False, mode)
         else:
             with torch.no_grad():
+                LAST_SOLVE["min_sample_residual"] = None
                 z, self.forward_res = self.solver(bound, init_point, **self.kwargs)
+                self.forward_min_sample_res = LAST_SOLVE["min_sample_residual"]
         if inference:
             with torch.no_grad():
                 z = bound(z)

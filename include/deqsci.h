@@ -212,6 +212,9 @@ typedef struct {
   int f_calls;         /* iterate-map evaluations that count towards the sigma schedule                */
   int converged;       /* 1 if the tolerance stopped the loop                                          */
   float sigma_next;    /* sigma the next call would use                                                */
+  double min_sample_residual; /* smallest PER-SAMPLE residual ||F_b-X_b||/(eps+||F_b||) over the counted iterations:
+                          below tol means a sample solved on its own (the reference's batch 1) would have stopped
+                          earlier than the whole-batch test did                                                   */
 } deqsci_solver_result;
 
 size_t deqsci_reconstruct_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T, int m);
@@ -242,6 +245,32 @@ size_t deqsci_adjoint_solve_workspace_bytes(int B, int H, int W, int T, int m);
 int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_sum, float* out,
                          const deqsci_solver_opts* opts, void* workspace, size_t workspace_bytes,
                          deqsci_solver_result* result, int B, int H, int W, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gradient exchange of the training step fused with the optimizer (csrc/optim.cu).  The reference has no
+ * distributed backend; this is the one exchange step data-parallel training adds between loss.backward() and
+ * optimizer.step() (training/sci_equilibrium_training.py:66-75; Adam(lr) built at video_sci_proxgrad.py:201).
+ *
+ * Every rank owns a communication buffer: [n_floats gradient | barrier flags], allocated by deqsci_comm_alloc
+ * and exported as a 64-byte CUDA IPC handle; peers map it with deqsci_comm_open.  deqsci_adam_allreduce_step
+ * launches ONE kernel: cross-GPU barrier, g = grad_scale * sum_r grad_r (P2P loads over NVLink, summed in rank
+ * order so every rank gets identical bits), torch.optim.Adam update (no weight decay / amsgrad) of this rank's
+ * params / exp_avg / exp_avg_sq, closing barrier.  comm_bases_host[r] = base of rank r's buffer as mapped in
+ * THIS process (own allocation for r = rank).  world = 1 (or a gradient already reduced by the caller, with
+ * comm_bases_host = {own}) is the plain fused Adam step.  `epoch` must grow by one per call on every rank
+ * (1, 2, ...); `step` is Adam's bias-correction step.  All ranks must make the call with the same n_floats.
+ * ---------------------------------------------------------------------------------------------- */
+size_t deqsci_comm_bytes(long long n_floats);
+int deqsci_comm_alloc(long long n_floats, void** dev_ptr, void* ipc_handle_64);
+int deqsci_comm_open(const void* ipc_handle_64, void** dev_ptr);
+int deqsci_comm_close(void* peer_ptr);
+int deqsci_comm_free(void* dev_ptr);
+/* error_host = 1 when a barrier of an earlier step timed out (a peer never arrived); synchronous copy. */
+int deqsci_comm_error(const void* comm_base, long long n_floats, int* error_host);
+int deqsci_adam_allreduce_step(float* params, float* exp_avg, float* exp_avg_sq,
+                               const void* const* comm_bases_host, int rank, int world, long long n_floats,
+                               float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                               unsigned epoch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Launch accounting and sampled device timing of the library's own kernels.

@@ -13,6 +13,17 @@ import numpy as np
 import torch
 
 REFERENCE_ROOT = os.environ.get("DEQSCI_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+
+
+def use_staged_reference() -> bool:
+    """Where /root/reference does not exist (the GPU box), import the reference's hot-path files from the tree
+    oracle/make_ref.py staged under oracle/_ref/ (git-ignored, travels with the working tree).  Returns
+    whether a reference tree is importable afterwards."""
+    global REFERENCE_ROOT
+    if not reference_available() and os.path.isdir(os.path.join(STAGED_ROOT, "solvers")):
+        REFERENCE_ROOT = STAGED_ROOT
+    return reference_available()
 
 
 def reference_available() -> bool:
@@ -35,6 +46,22 @@ def skimage_psnr(image_true, image_test, data_range=None):
 
 
 _installed = False
+
+
+class cpu_only:
+    """Context manager: the reference hard-codes .cuda() (solvers/equilibrium_solvers_yaping.py:394,410); on a box
+    WITH a GPU its CPU run needs those calls to be no-ops.  Patches torch.Tensor.cuda / nn.Module.cuda to identity
+    for the duration of the block and restores them (bench.py's CPU legs run next to the GPU arm)."""
+
+    def __enter__(self):
+        self._saved = (torch.Tensor.cuda, torch.nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda, torch.nn.Module.cuda = self._saved
+        return False
 
 
 def install_shims():
@@ -69,7 +96,7 @@ def install_shims():
     _installed = True
 
 
-def build_reference_deq(denoiser: str, max_iter: int, m: int = 5, beta: float = 1.0):
+def build_reference_deq(denoiser: str, max_iter: int, m: int = 5, beta: float = 1.0, state_dict=None):
     """Builds the reference objects exactly as video_sci_proxgrad.py:145-245 does (inference).
 
     denoiser in {'ffdnet', 'SimpleCNN', 'RealSN_SimpleCNN'}; weights: models/cnn.ckpt,
@@ -98,7 +125,7 @@ def build_reference_deq(denoiser: str, max_iter: int, m: int = 5, beta: float = 
     net.eval()
     solver = EquilibriumProxGradSCI(A=A_torch_, At=At_torch_, nonlinear_operator=net, eta=0.2,
                                     minval=-1, maxval=1)
-    sd = reference_state_dict(denoiser)
+    sd = state_dict if state_dict is not None else reference_state_dict(denoiser)
     solver.load_state_dict(sd)
     deq = eq_utils.DEQFixedPoint(solver, eq_utils.andersonexp, m=m, beta=beta, lam=1e-2,
                                  max_iter=max_iter, tol=1e-5)

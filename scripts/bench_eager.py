@@ -22,19 +22,21 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--tf32", type=int, default=1)
-    ap.add_argument("--max-iter", type=int, default=180)
-    ap.add_argument("--reps", type=int, default=2)
-    a = ap.parse_args()
-    torch.backends.cudnn.allow_tf32 = bool(a.tf32)
-    torch.backends.cuda.matmul.allow_tf32 = bool(a.tf32)
-    dev = torch.device("cuda", 0)
-    solver, _ = bench.build_deq(dev, "fp32")
+def run(dev, y, Phi, tf32, max_iter=180, reps=2, weights_solver=None):
+    """Reconstructs the batch (y [B,H,W], Phi [B,H,W,T]) with the restated eager call sequence; returns recon/s
+    (mean over `reps` after one warm-up).  TF32 flags are restored afterwards."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    try:
+        return _run(dev, y, Phi, max_iter, reps, weights_solver)[0]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _run(dev, y, Phi, max_iter, reps, weights_solver=None):
+    solver = weights_solver or bench.build_deq(dev, "fp32")[0]
     seq = solver.nonlinear_op.intermediate_dncnn.itermediate_dncnn       # torch layers = weight containers
-    y, Phi, _ = (t.to(dev) for t in bench.synthetic_batch(0, a.batch))
     Phi_sum = torch.sum(Phi, dim=3)
     Phi_sum[Phi_sum == 0] = 1
     state = {"sigma": None, "ymean": None}
@@ -66,6 +68,7 @@ def main():
         rhs = torch.zeros(bsz, m + 1, 1, device=dev)
         rhs[:, 0] = 1
         k = 1
+        res = None
         for k in range(2, max_iter):
             n = min(k, m)
             G = Fh[:, :n] - X[:, :n]
@@ -79,14 +82,15 @@ def main():
         return X[:, k % m].view_as(x0), res
 
     times = []
+    res = None
     with torch.no_grad():
-        for rep in range(a.reps + 1):
+        for rep in range(reps + 1):
             state["ymean"] = None
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             x0 = y[:, :, :, None] * Phi
-            zs, res = andersonexp(x0, max_iter=a.max_iter)
+            zs, res = andersonexp(x0, max_iter=max_iter)
             z = f(zs)
             f(z)                                # the reference's second post-solver call
             e1.record()
@@ -94,8 +98,23 @@ def main():
             if rep > 0:
                 times.append(e0.elapsed_time(e1))
     ms = sum(times) / len(times)
+    return y.shape[0] * 1e3 / ms, ms, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--tf32", type=int, default=1)
+    ap.add_argument("--max-iter", type=int, default=180)
+    ap.add_argument("--reps", type=int, default=2)
+    a = ap.parse_args()
+    torch.backends.cudnn.allow_tf32 = bool(a.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(a.tf32)
+    dev = torch.device("cuda", 0)
+    y, Phi, _ = (t.to(dev) for t in bench.synthetic_batch(0, a.batch))
+    rps, ms, res = _run(dev, y, Phi, a.max_iter, a.reps)
     print(json.dumps({"impl": "pytorch eager on GPU (restated reference call sequence)", "tf32": bool(a.tf32),
-                      "batch": a.batch, "ms_per_batch": ms, "recon_per_s": a.batch * 1e3 / ms, "res": res}))
+                      "batch": a.batch, "ms_per_batch": ms, "recon_per_s": rps, "res": res}))
 
 
 if __name__ == "__main__":

@@ -38,46 +38,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     from deqsci_b200 import _lib
-    from deqsci_b200.distributed import allreduce_mean_gradients, max_over_ranks, shard_range
-    from deqsci_b200.utils.cg_utils import Phi_sum_, initial_point
     _lib.lib()
-    solver, deq = bench.build_deq(dev, "tc_split", args.denoiser, args.max_iter)
-    solver.train()
-    solver.nonlinear_op.train()
-    opt = torch.optim.Adam(solver.parameters(), lr=1e-4)
-    lo, hi = shard_range(world * args.batch, rank, world)
-    y, phi, gt = (t.to(dev) for t in bench.synthetic_batch(lo, hi - lo))
-    loss_fn = torch.nn.MSELoss(reduction="mean")
-    ar_ms, step_ms, losses = [], [], []
-    for it in range(args.warmup + args.steps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record()
-        opt.zero_grad()
-        phi_sum = Phi_sum_(phi)
-        rec = deq.forward(y, phi, phi_sum, initial_point=initial_point(y, phi, phi_sum, gt))
-        loss = loss_fn(rec, gt)
-        loss.backward()
-        e[1].record()
-        n = allreduce_mean_gradients(solver.parameters())
-        e[2].record()
-        opt.step()
-        e[3].record()
-        torch.cuda.synchronize()
-        if it >= args.warmup:
-            step_ms.append(max_over_ranks(e[0].elapsed_time(e[3]), dev))
-            ar_ms.append(max_over_ranks(e[1].elapsed_time(e[2]), dev))
-            losses.append(float(loss.detach()))
+    r = bench.train_step_bench(dev, rank, world, steps=args.steps, warmup=args.warmup, batch=args.batch,
+                               max_iter=args.max_iter, denoiser=args.denoiser)
     if rank == 0:
-        print(json.dumps({"metric": "DE-GAP-%s implicit-diff training step" % args.denoiser, "n_gpus": world,
-                          "batch_per_gpu": args.batch, "and_maxiters": args.max_iter,
-                          "ms_per_step": float(np.mean(step_ms)), "allreduce_ms": float(np.mean(ar_ms)),
-                          "allreduce_floats": int(n), "steps_per_s": 1e3 / float(np.mean(step_ms)),
-                          "measurements_per_s": world * args.batch * 1e3 / float(np.mean(step_ms)),
-                          "forward_res": deq.forward_res, "backward_res": deq.backward_res, "loss": losses,
-                          "native": "forward solve (train-mode BatchNorm kernels), backward Anderson solve + GAP VJP; the one graph-attached f call on cuDNN fp32"}))
+        r["native"] = ("forward solve (train-mode BatchNorm kernels), backward Anderson solve + GAP VJP, gradient exchange + "
+                       "Adam (one kernel); the one graph-attached f call on cuDNN fp32")
+        print(json.dumps(r))
     if world > 1:
         dist.destroy_process_group()
 

@@ -246,6 +246,79 @@ def stage_realsn_dncnn():
     print("realsn_dncnn", y_eval.shape, float(y_eval.abs().max()), float(y_train.detach().abs().max()))
 
 
+def stage_admm():
+    """EquilibriumADMMSCI + admmexp + DEQFixedPointADMM (reference solvers/equilibrium_solvers_yaping.py:438-465,
+    solvers/new_equilibrium_utils_yaping.py:396-451) on the 64x64 traffic crop, B=2, two single steps and a 4-step solve, with the
+    one-argument frame denoiser the class supports: SimpleCNN weights (cnn.ckpt) and `conv3d = False` set by
+    hand (the reference's DnCNN lacks the attribute)."""
+    ref_import.install_shims()
+    from solvers.equilibrium_solvers_yaping import EquilibriumADMMSCI
+    from solvers import new_equilibrium_utils_yaping as eq
+    from utils.cg_utils import A_torch_, At_torch_
+    small = dict(np.load(os.path.join(HERE, "small_vectors.npz")))
+    Phi_c, y_c = torch.from_numpy(small["crop_Phi"]), torch.from_numpy(small["crop_y"])
+    Phi_sum_c = torch.sum(Phi_c, axis=3)
+    Phi_sum_c[Phi_sum_c == 0] = 1
+    solver0, _ = ref_import.build_reference_deq("SimpleCNN", max_iter=10)
+    net = solver0.nonlinear_op
+    net.conv3d = False
+    f = EquilibriumADMMSCI(A_torch_, At_torch_, net, eta=0.2)
+    x0 = At_torch_(y_c, Phi_c)
+    out = {}
+    with torch.no_grad():
+        z1, u1 = f(x0, torch.zeros_like(x0), y_c, Phi_c, Phi_sum_c)
+        z2, u2 = f(z1, u1, y_c, Phi_c, Phi_sum_c)
+        out["z1"], out["u1"], out["z2"], out["u2"] = z1.numpy(), u1.numpy(), z2.numpy(), u2.numpy()
+        deq = eq.DEQFixedPointADMM(f, eq.admmexp, eq.admmexp, m=5, beta=1.0, lam=1e-2, max_iter=6, tol=1e-5)
+        z = deq.forward(y_c, Phi_c, Phi_sum_c, initial_point=[x0, torch.zeros_like(x0)], train_flag=False)
+        out["deq_z"], out["deq_res"] = z.numpy(), np.array(deq.forward_res)
+    np.savez_compressed(os.path.join(HERE, "admm_vectors.npz"), **out)
+    print("admm: res", deq.forward_res, "|z|", float(z.norm()))
+
+
+def stage_synthetic(count=2):
+    """VERDICT r01 missing #4: the reference itself on the workload bench.py times -- measurements 0..count-1 of
+    bench.synthetic_batch (kind = bench.DATA_KIND), DE-GAP-FFDnet, 180 iterations, batch 1 each: PSNR, SSIM,
+    residual, the norm of the input of every iterate-map call, 64x64x8 crops of the inputs of calls
+    2, 20, 40, 100 and 180 and of the reconstruction.  ~150 s per measurement on 8 threads."""
+    ref_import.install_shims()
+    import pytorch_ssim
+    from utils.cg_utils import At_torch_
+    import bench
+    ys, ps, xs = bench.synthetic_batch(0, count)
+    out = {"kind": np.array(bench.DATA_KIND), "seed": np.array(bench.SEED)}
+    for i in range(count):
+        y, Phi, g = ys[i:i + 1], ps[i:i + 1], xs[i:i + 1]
+        Phi_sum = torch.sum(Phi, axis=3)
+        Phi_sum[Phi_sum == 0] = 1
+        solver, deq = ref_import.build_reference_deq("ffdnet", max_iter=180)
+        zin = []
+        keep = {}
+        def hook(mod, args):
+            k = len(zin)
+            zin.append(float(args[0].detach().norm()))
+            if k in (2, 20, 40, 100, 180):
+                keep[k] = args[0].detach()[0][CROP].numpy().copy()
+        h = solver.register_forward_pre_hook(hook)
+        t0 = time.time()
+        z = deq.forward(y, Phi, Phi_sum, initial_point=At_torch_(y, Phi), train_flag=False).detach()
+        h.remove()
+        rec = z.clip(0, 1)
+        key = "m%d" % i
+        out[key + "_psnr"] = np.array(ref_import.skimage_psnr(g.numpy(), rec.numpy()))
+        out[key + "_ssim"] = np.array(float(pytorch_ssim.ssim(rec.permute(0, 3, 1, 2).contiguous(),
+                                                                g.permute(0, 3, 1, 2).contiguous())))
+        out[key + "_res"] = np.array(deq.forward_res)
+        out[key + "_innorm"] = np.array(zin)
+        out[key + "_ymean"] = np.array(float(y.mean()))
+        for k, v in keep.items():
+            out[key + "_in%d_crop" % k] = v
+        out[key + "_z_crop"] = z[0][CROP].numpy()
+        print(key, "psnr %.4f ssim %.5f res %.3e calls %d  %.1fs" % (out[key + "_psnr"], out[key + "_ssim"],
+                                                                     deq.forward_res, len(zin), time.time() - t0), flush=True)
+        np.savez_compressed(os.path.join(HERE, "synthetic_recon.npz"), **out)
+
+
 def stage_train(wide=False):
     """One implicit-differentiation training step (reference training/sci_equilibrium_training.py:54-75)
     on a 32x32x8 crop (wide: 32x160x8, large enough for the native train-mode kernels), B=2,
@@ -291,7 +364,7 @@ def stage_train(wide=False):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "train_wide", "dncnn_bn", "realsn_dncnn"])
+    ap.add_argument("--stage", required=True, choices=["assets", "small", "full", "train", "train_wide", "dncnn_bn", "realsn_dncnn", "admm", "synthetic"])
     ap.add_argument("--denoisers", nargs="*", default=DENOISERS)
     ap.add_argument("--scenes", nargs="*", default=SCENES)
     a = ap.parse_args()
@@ -308,5 +381,9 @@ if __name__ == "__main__":
         stage_dncnn_bn()
     elif a.stage == "realsn_dncnn":
         stage_realsn_dncnn()
+    elif a.stage == "admm":
+        stage_admm()
+    elif a.stage == "synthetic":
+        stage_synthetic()
     else:
         stage_full(a.denoisers, a.scenes)

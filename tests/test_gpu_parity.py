@@ -27,6 +27,20 @@ def dev():
     return torch.device("cuda", 0)
 
 
+GRAD_TESTS = {"test_eval_mode_with_grad_builds_the_graph"}
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode(request):
+    """These are inference parity tests: grad mode off (what selects the native kernels for direct module
+    calls since eval mode alone no longer does) -- except the tests that check the graph path."""
+    if request.node.originalname in GRAD_TESTS:
+        yield
+    else:
+        with torch.no_grad():
+            yield
+
+
 def t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
@@ -455,6 +469,56 @@ def test_full_scene_psnr_vs_reference(dev, full_recon, d, scene):
     assert rel_l2(crop, full_recon[key + "_z_crop"]) <= 1e-3
 
 
+def test_benchmark_workload_vs_reference(dev):
+    """VERDICT r01 missing #4 / SURVEY 8(d) 'parity subset': the workload bench.py times -- measurements 0 and 1 of
+    bench.synthetic_batch, DE-GAP-FFDnet, 180 iterations -- against the reference's own run of the same two
+    measurements (tests/golden/synthetic_recon.npz, make_golden.py --stage synthetic).  Bars: north-star
+    1e-3 per iterate / 0.05 dB / 1e-3 SSIM; the iterates after call ~60 are compared at 5e-3 because on this
+    data two fp32 runs of the SAME code already differ by 3.7e-4 .. 1.6e-3 there (tests/tools/emulate_gpu.py,
+    'jitter' rows of profiles/r02_precision_emulation.md)."""
+    import bench
+    from conftest import GOLDEN
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    g = dict(np.load(os.path.join(GOLDEN, "synthetic_recon.npz")))
+    assert str(g["kind"]) == bench.DATA_KIND and int(g["seed"]) == bench.SEED, "golden made for another generator"
+    ys, ps, xs = bench.synthetic_batch(0, 2)
+    assert abs(float(ys[0].mean()) - float(g["m0_ymean"])) < 1e-6        # same synthetic data as the reference saw
+    solver = build_solver("ffdnet", dev)
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=180, tol=1e-5)
+    y, Phi = ys.to(dev), ps.to(dev)
+    seen = []
+    hk = solver.register_forward_pre_hook(lambda mod, args: seen.append(args[0].detach().clone()))
+    z = deq.forward(y, Phi, Phi_sum_(Phi), initial_point=At_torch_(y, Phi), train_flag=False)
+    hk.remove()
+    assert len(seen) == 181
+    report = {}
+    for i in range(2):
+        key = "m%d" % i
+        norms = np.array([float(s_[i].double().norm()) for s_ in seen])
+        dev_n = np.abs(norms - g[key + "_innorm"][:181]) / g[key + "_innorm"][:181]
+        assert dev_n[:41].max() <= 1e-4 and dev_n.max() <= 2e-3, (i, dev_n[:41].max(), dev_n.max())
+        rel = {}
+        for k in (2, 20, 40, 100, 180):
+            rel[k] = rel_l2(seen[k][i, 96:160, 96:160].cpu().numpy(), g[key + "_in%d_crop" % k])
+            assert rel[k] <= (1e-3 if k <= 40 else 5e-3), (i, k, rel[k])
+        rel["z"] = rel_l2(z[i, 96:160, 96:160].cpu().numpy(), g[key + "_z_crop"])
+        assert rel["z"] <= 5e-3
+        rec = z[i:i + 1].clip(0, 1).cpu().numpy()
+        gt = xs[i:i + 1].numpy()
+        psnr = orc.psnr(gt, rec)
+        ssim = orc.ssim(rec.transpose(0, 3, 1, 2), gt.transpose(0, 3, 1, 2))
+        assert abs(psnr - float(g[key + "_psnr"])) <= 0.05, (psnr, float(g[key + "_psnr"]))
+        assert abs(ssim - float(g[key + "_ssim"])) <= 1e-3
+        report[key] = {"rel_l2_crops": {str(k): float(v) for k, v in rel.items()}, "dpsnr": psnr - float(g[key + "_psnr"]),
+                       "dssim": ssim - float(g[key + "_ssim"]), "max_norm_dev_first41": float(dev_n[:41].max()),
+                       "max_norm_dev": float(dev_n.max())}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        import json
+        json.dump(report, open(os.path.join(out_dir, "parity_report_synthetic.json"), "w"), indent=1)
+
+
 def test_sigma_schedule_resets_for_function_scoped_measurements(dev, full_recon):
     """drop8 then runner8, each measurement a function-scoped tensor (the caching allocator
     hands the second one the address the first just freed).  The schedule must reset by VALUE (reference
@@ -506,6 +570,33 @@ def test_eval_mode_with_grad_builds_the_graph(dev, small_vectors):
     assert deq.backward_res is not None
 
 
+def test_admm_sci_golden(dev, small_vectors):
+    """EquilibriumADMMSCI + admmexp + DEQFixedPointADMM on the native GAP step (z+u, Phi_sum + 1e-8) and
+    the native denoiser in 'replace' mode, against the reference's own run (tests/golden/admm_vectors.npz).  As in
+    the reference the one-argument frame denoiser needs `conv3d = False` set by hand (its DnCNN lacks the attribute)."""
+    from conftest import GOLDEN
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.solvers.equilibrium_solvers_yaping import EquilibriumADMMSCI
+    from deqsci_b200.utils.cg_utils import A_torch_, At_torch_, Phi_sum_
+    g = dict(np.load(os.path.join(GOLDEN, "admm_vectors.npz")))
+    v = small_vectors
+    Phi, y = t(v["crop_Phi"], dev), t(v["crop_y"], dev)
+    Ps, x0 = Phi_sum_(Phi), At_torch_(y, Phi)
+    net = build_solver("SimpleCNN", dev).nonlinear_op
+    f = EquilibriumADMMSCI(A_torch_, At_torch_, net, eta=0.2)
+    with pytest.raises(AttributeError):                       # same failure as the reference without the attribute
+        f(x0, torch.zeros_like(x0), y, Phi, Ps)
+    net.conv3d = False
+    z1, u1 = f(x0, torch.zeros_like(x0), y, Phi, Ps)
+    z2, u2 = f(z1, u1, y, Phi, Ps)
+    for got, key in ((z1, "z1"), (u1, "u1"), (z2, "z2"), (u2, "u2")):
+        assert rel_l2(got.cpu().numpy(), g[key]) <= 1e-4, key
+    deq = eq.DEQFixedPointADMM(f, eq.admmexp, eq.admmexp, m=5, beta=1.0, lam=1e-2, max_iter=6, tol=1e-5)
+    z = deq.forward(y, Phi, Ps, initial_point=[x0, torch.zeros_like(x0)], train_flag=False)
+    assert rel_l2(z.cpu().numpy(), g["deq_z"]) <= 1e-3
+    assert abs(deq.forward_res - float(g["deq_res"])) <= 1e-3 * float(g["deq_res"])
+
+
 # ---------------------------------------------------------------------------------------------
 # (6) the caller: test_solver_sci over all benchmark scenes present (configs 2 and 3)
 # ---------------------------------------------------------------------------------------------
@@ -523,8 +614,8 @@ def _psnr_tol(d, scene):
 @pytest.mark.parametrize("d", DENOISERS)
 def test_solver_sci_all_scenes_vs_reference(dev, full_recon, d):
     """All 8 benchmark measurements (drop8, runner8, traffic x6) through the mirrored
-    test_solver_sci (one batched solve per scene): per-measurement PSNR / SSIM against the
-    reference's own run, and the reported average against the reference's."""
+    test_solver_sci (ONE batched solve over all scenes, device-side PSNR / SSIM): per-measurement PSNR / SSIM
+    against the reference's own run, and the reported average against the reference's."""
     from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
     from deqsci_b200.training import sci_equilibrium_training as tr
     from deqsci_b200.utils.metrics import peak_signal_noise_ratio, ssim
@@ -542,6 +633,8 @@ def test_solver_sci_all_scenes_vs_reference(dev, full_recon, d):
     avg, images = tr.test_solver_sci(deq, samples, save_img_path=None, verbose=False, save_image=False, device=dev)
     assert abs(avg - float(np.mean(want_scene))) <= (0.1 if d == "ffdnet" else 0.05)
     assert len(images) == 8 * 8                                   # one [H,W,1] array per frame
+    assert deq.forward_min_sample_res is not None and deq.forward_min_sample_res <= deq.forward_res * 1.0001
+    dev_metrics = tr.test_solver_sci.last_metrics                 # reduced on the device
     k0 = "drop8_cacti.mat_reconstruction_0.png"
     assert images[k0].shape == (256, 256, 1) and images[k0].max() <= 255.0
     report = []
@@ -556,8 +649,48 @@ def test_solver_sci_all_scenes_vs_reference(dev, full_recon, d):
             ds = float(ssim(torch.from_numpy(rec.astype(np.float32)).permute(2, 0, 1)[None],
                             torch.from_numpy(g).permute(2, 0, 1)[None])) - float(full_recon["%s_%s_%d_ssim" % (d, scene, fi)])
             report.append((scene, fi, round(dp, 4), round(ds, 5)))
+            m_dev = dev_metrics[scene + "_cacti.mat"]
+            assert abs(m_dev["psnr"][fi] - peak_signal_noise_ratio(g, rec)) <= 2e-3        # device vs host metric
+            assert abs(m_dev["ssim"][fi] - (ds + float(full_recon["%s_%s_%d_ssim" % (d, scene, fi)]))) <= 2e-4
             assert abs(dp) <= tol_p and abs(ds) <= tol_s, report
     print("dPSNR/dSSIM vs reference:", report)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):                                    # evidence for profiles/ (scratch dir on the GPU box)
+        import json
+        with open(os.path.join(out_dir, "parity_report_%s.json" % d), "w") as fh:
+            json.dump([{"scene": a, "meas": b, "dpsnr": c, "dssim": e} for a, b, c, e in report], fh)
+
+
+def test_solver_sci_stops_per_measurement_like_the_reference(dev, small_vectors):
+    """the reference solves and STOPS each measurement on its own (batch 1, whole-batch residual =
+    that sample's).  With a tolerance that fires, the batched test_solver_sci must fall back to per-measurement
+    solves and return exactly what the reference's loop structure returns; metrics come back per measurement."""
+    from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
+    from deqsci_b200.training import sci_equilibrium_training as tr
+    from deqsci_b200.utils.cg_utils import At_torch_, Phi_sum_
+    v = small_vectors
+    d = "SimpleCNN"
+    tol = 2e-2
+    sample = {"gt": torch.from_numpy(np.concatenate([v["crop_gt"][0], v["crop_gt"][1]], axis=2))[None],
+              "mask": torch.from_numpy(v["crop_Phi"][:1]), "meas": torch.from_numpy(v["crop_y"].transpose(1, 2, 0))[None],
+              "file": ["traffic_crop.mat"]}
+    solver = build_solver(d, dev)
+    deq = eq.DEQFixedPoint(solver, eq.andersonexp, m=5, beta=1.0, lam=1e-2, max_iter=40, tol=tol)
+    avg, images = tr.test_solver_sci(deq, [sample], save_img_path=None, verbose=False, save_image=False, device=dev)
+    assert set(tr.test_solver_sci.last_metrics["traffic_crop.mat"]) == {"psnr", "ssim"}
+    assert len(tr.test_solver_sci.last_metrics["traffic_crop.mat"]["psnr"]) == 2
+    # the reference's structure: one solve per measurement
+    Phi = t(v["crop_Phi"][:1], dev)
+    Ps = Phi_sum_(Phi)
+    iters = []
+    for fi in range(2):
+        y = t(v["crop_y"][fi:fi + 1], dev)
+        z = deq.forward(y, Phi, Ps, initial_point=At_torch_(y, Phi), train_flag=False)
+        iters.append(deq.forward_res)
+        want = z.clip(0, 1).cpu().numpy()[0]
+        got = np.stack([images["traffic_crop.mat_reconstruction_%d.png" % (fi * 8 + k)][:, :, 0] for k in range(8)], 2) / 255.0
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    assert min(iters) < tol                                      # the stopping test really fired
 
 
 # ---------------------------------------------------------------------------------------------

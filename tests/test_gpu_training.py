@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, load_weights, rel_l2
+from conftest import GOLDEN, ROOT, load_weights, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -202,3 +202,27 @@ def test_plan_refresh_on_device_equals_rebuild(d):
     assert fresh.native_plan(dev, train=train) is not plan0
     assert torch.equal(got, want)
     assert not torch.equal(got, before)
+
+
+def test_fused_scale_adam_single_gpu():
+    """GradientSynchronizer at world 1: flat in-place gradients + ONE fused scale + Adam kernel equals
+    torch.optim.Adam step for step; an adopted torch optimizer keeps a meaningful state_dict (csrc/optim.cu)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fused_adam_check.py")], capture_output=True,
+                       text=True, timeout=300)
+    assert "FUSED_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_fused_allreduce_adam_two_gpus():
+    """Two ranks: the ONE-kernel exchange (cross-GPU barrier + one-shot all-reduce over NVLink peer memory + 1/world
+    scale + Adam) and its NCCL variant both equal all-gather-mean + torch Adam, and the ranks' parameter copies stay
+    bitwise identical."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29653",
+                        os.path.join(ROOT, "scripts", "fused_adam_check.py")], capture_output=True, text=True, timeout=600)
+    assert "FUSED_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -106,3 +106,41 @@ def test_noise_floor_fixture():
     assert max(diffs) > 0.25 and min(diffs) < 0.05
     assert all(float(v["traffic_%d_norm_rel_dev" % i].max()) > 1e-3 for i in (1, 2, 5))
     assert all(float(v["traffic_%d_norm_rel_dev" % i][:30].max()) < 1e-4 for i in (1, 2, 5))   # early iterates agree
+
+
+def test_admm_sci(small_vectors):
+    """EquilibriumADMMSCI / admmexp restatement vs the reference's own run (tests/golden/admm_vectors.npz,
+    make_golden.py --stage admm; reference solvers/equilibrium_solvers_yaping.py:438-465,
+    solvers/new_equilibrium_utils_yaping.py:396-451)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "admm_vectors.npz")))
+    y, Phi, Ps, x0 = _crop_inputs(small_vectors)
+    f = orc.ADMMSCI(load_weights("SimpleCNN"))
+    z1, u1 = f(x0, np.zeros_like(x0), y, Phi, Ps)
+    z2, u2 = f(z1, u1, y, Phi, Ps)
+    for got, key in ((z1, "z1"), (u1, "u1"), (z2, "z2"), (u2, "u2")):
+        assert rel_l2(got, g[key]) <= 2e-5, key
+    z, u, res = orc.admmexp(lambda a, b: f(a, b, y, Phi, Ps), [x0, np.zeros_like(x0)], m=5, lam=1e-2, max_iter=6,
+                            tol=1e-5, beta=1.0)
+    assert rel_l2(z, g["deq_z"]) <= 1e-4
+    assert abs(res - float(g["deq_res"])) <= 1e-4 * float(g["deq_res"])
+
+
+def test_benchmark_workload_first_calls():
+    """The oracle on the workload bench.py times (bench.synthetic_batch measurement 0, full 256x256x8): the inputs
+    of the first 6 iterate-map calls have the norms the reference's own run recorded (synthetic_recon.npz)."""
+    import os
+    import bench
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "synthetic_recon.npz")))
+    assert str(g["kind"]) == bench.DATA_KIND
+    ys, ps, _ = bench.synthetic_batch(0, 1)
+    y, Phi = ys.numpy(), ps.numpy()
+    f = orc.ProxGradSCI("ffdnet", load_weights("ffdnet"))
+    orc.set_conv_backend("torch")
+    seen = []
+    fm = lambda z, *a: (seen.append(float(np.linalg.norm(z.astype(np.float64)))), f(z, *a))[1]
+    Ps = orc.phi_sum(Phi)
+    orc.andersonexp(lambda z: fm(z, y, Phi, Ps), orc.At(y, Phi), m=5, lam=1e-2, max_iter=6, tol=1e-5, beta=1.0)
+    np.testing.assert_allclose(np.array(seen), g["m0_innorm"][:6], rtol=2e-5)
