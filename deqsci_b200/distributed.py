@@ -51,6 +51,16 @@ def max_over_ranks(value, device="cpu"):
     return float(t.item())
 
 
+def min_over_ranks(value, device="cpu"):
+    """min of a python float over ranks (e.g. the exchange time seen by the LAST rank to arrive = no waiting)."""
+    rank, ws = world()
+    if ws == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
 def gather_floats(values, device="cpu"):
     """All ranks' lists of floats concatenated in rank order (e.g. per-measurement PSNRs)."""
     rank, ws = world()

@@ -58,6 +58,38 @@ def conv(x, w):
     return F.conv2d(x, w, padding=1)
 
 
+# ---- Winograd F(2x2, 3x3): 16 multiplies per 2x2 output tile and (cin, cout) pair instead of 36 ----------------
+_BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float32)
+_G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float32)
+_AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float32)
+
+
+def winograd_conv(x, w, split):
+    """3x3 pad-1 convolution through F(2x2,3x3) with fp32 transforms; the 16 batched [tiles x cin] . [cin x cout]
+    products run either in fp32 (split=False: transform rounding alone) or as the product's fp16 x 3 scheme on the
+    TRANSFORMED operands (what a tensor-core Winograd kernel would issue)."""
+    N, C, H, W = x.shape
+    O = w.shape[0]
+    dev = x.device
+    BT, G, AT = _BT.to(dev), _G.to(dev), _AT.to(dev)
+    U = torch.einsum("ij,ocjk,lk->ocil", G, w, G)                       # [O,C,4,4]
+    xp = F.pad(x, (1, 1, 1, 1))
+    tiles = xp.unfold(2, 4, 2).unfold(3, 4, 2)                          # [N,C,H/2,W/2,4,4]
+    V = torch.einsum("ij,nchwjk,lk->nchwil", BT, tiles, BT)             # [N,C,th,tw,4,4]
+    th, tw = V.shape[2], V.shape[3]
+    Vm = V.permute(4, 5, 0, 2, 3, 1).reshape(16, N * th * tw, C)        # [16, tiles, C]
+    Um = U.permute(2, 3, 1, 0).reshape(16, C, O)                        # [16, C, O]
+    if split:
+        vh, uh = q16(Vm), q16(Um)
+        vl, ul = q16((Vm - vh) * S), q16((Um - uh) * S)
+        M = torch.bmm(vh, uh) + (torch.bmm(vh, ul) + torch.bmm(vl, uh)) / S
+    else:
+        M = torch.bmm(Vm, Um)
+    M = M.reshape(4, 4, N, th, tw, O)
+    Y = torch.einsum("ij,jknhwo,lk->nohiwl", AT, M, AT)                 # [N,O,th,2,tw,2]
+    return Y.reshape(N, O, th * 2, tw * 2)
+
+
 class Emu:
     """conv3x3(x, w) for hidden layers under a named operand scheme."""
 
@@ -89,6 +121,10 @@ class Emu:
             return conv(x, w)
         if m == "jitter":                             # fp32 noise floor: 6e-8 relative input jitter
             return conv(x * (1 + 6e-8 * torch.randn_like(x)), w)
+        if m == "wino_fp32":
+            return winograd_conv(x, w, False)
+        if m == "wino_split":
+            return winograd_conv(x, w, True)
         d = self.weights(w)
         ah = q16(x)
         main = conv(ah, d["wh"])
