@@ -68,6 +68,12 @@ SIGNATURES = {
     "deqsci_adjoint_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "deqsci_adjoint_solve": (c_int, [_P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
                                      c_int, c_int, c_int, c_int, _P]),
+    "deqsci_denoiser_activation_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "deqsci_iterate_save": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int,
+                                    c_int, _P]),
+    "deqsci_denoise_residual_masked": (c_int, [_P, _P, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int, c_int, _P]),
+    "deqsci_adjoint_solve_denoiser": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t,
+                                              POINTER(SolverResult), c_int, c_int, c_int, c_int, _P]),
     "deqsci_comm_bytes": (c_size_t, [c_longlong]),
     "deqsci_comm_alloc": (c_int, [c_longlong, POINTER(_P), _P]),
     "deqsci_comm_open": (c_int, [_P, POINTER(_P)]),

@@ -44,7 +44,7 @@ void tcf_pack_map(int cin, int32_t* map);
 bool tcf_supported(int Wc);
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
-                         int Wc, cudaStream_t st);
+                         int Wc, cudaStream_t st, const __half* mask = nullptr);
 size_t tcl_weight_image_bytes();
 void tcl_pack_weights(const float* w, int cout, uint8_t* img);
 void tcl_pack_map(int cout, int32_t* map);
@@ -58,7 +58,7 @@ void tc2_pack_map(int32_t* map);
 bool tc2_supported(int Hc, int Wc);
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                            cudaStream_t st, double* stats = nullptr);
+                            cudaStream_t st, double* stats = nullptr, const __half* mask = nullptr);
 int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift,
                     const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
@@ -308,10 +308,14 @@ extern "C" size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int 
   return 1024 + g.zprime_bytes + 2 * g.act_bytes + kTrainScratchBytes;
 }
 
+// save  (optional, num_layers-1 entries): layer i writes its output planes to save[i] instead of the ping-pong
+//       buffers (and layer i+1 reads them): the activations a backward pass needs.
+// masks (optional, num_layers-1 entries): layer i's output is gated by the sign of masks[i] (a saved activation's hi
+//       plane) instead of ReLU -- the adjoint stack of a conv / ReLU network (tensor-core kernels only).
 static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, const float* y, const float* phi,
                      const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes, int B,
                      int H, int W, int T, void* stream, const deqsci_bn_params* bn = nullptr, float momentum = 0.f,
-                     float eps = 0.f) {
+                     float eps = 0.f, void* const* save = nullptr, const void* const* masks = nullptr) {
   Geometry g;
   int rc = geometry(h, B, H, W, T, &g);
   if (rc) return rc;
@@ -328,6 +332,19 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
                     reinterpret_cast<__half*>(ws + g.zprime_bytes + g.act_bytes)};
   cudaStream_t st = (cudaStream_t)stream;
   const int nl = (int)h->layers.size();
+  if (save)
+    for (int i = 0; i < nl - 1; ++i) DEQSCI_CHECK_ARG(save[i] != nullptr, "activation buffer of layer %d is null", i);
+  if (masks) {
+    for (int i = 0; i < nl - 1; ++i) DEQSCI_CHECK_ARG(masks[i] != nullptr, "mask plane of layer %d is null", i);
+    DEQSCI_CHECK_ARG(!bn && h->precision == DEQSCI_PREC_TC_SPLIT && tcf_supported(g.Wc) && tc2_supported(g.Hc, g.Wc),
+                     "masked (adjoint) stacks need precision tc_split and conv images wider than 64 pixels (got %dx%d)",
+                     g.Hc, g.Wc);
+  }
+  // output buffer of conv layer i / input buffer of conv layer i (i >= 1)
+  auto out_buf = [&](int i, int cur) { return save ? reinterpret_cast<__half*>(save[i]) : act[cur ^ 1]; };
+  auto in_buf = [&](int i, int cur) { return save ? reinterpret_cast<__half*>(save[i - 1]) : act[cur]; };
+  auto mask_of = [&](int i) { return masks ? reinterpret_cast<const __half*>(masks[i]) : nullptr; };
+  auto relu_of = [&](int i, int relu) { return masks ? 2 : relu; };
   double* bn_stats = reinterpret_cast<double*>(ws + g.zprime_bytes + 2 * g.act_bytes);      // [kMaxStatCtas][128]
   float* bn_scale_shift = reinterpret_cast<float*>(bn_stats + (size_t)kMaxStatCtas * 2 * kHidden);   // [128]
   if (bn) {
@@ -349,45 +366,48 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap,
                          zprime_planar, st);
     if (rc) return rc;
-    rc = conv_first_tc_launch(act[1], in_plane, act[0], g.plane_elems, L0.w_tc, L0.scale, L0.bias, L0.relu, g.NF,
-                              g.Hc, g.Wc, st);
+    rc = conv_first_tc_launch(act[1], in_plane, save ? reinterpret_cast<__half*>(save[0]) : act[0], g.plane_elems,
+                              L0.w_tc, L0.scale, L0.bias, relu_of(0, L0.relu), g.NF, g.Hc, g.Wc, st, mask_of(0));
   } else {
     rc = conv_first_launch(h->kind, fuse_gap, z, y, phi, phi_sum, zprime_ws, sigma, L0.w_cc, L0.scale, L0.bias,
-                           L0.relu, act[0], g.plane_elems, B, H, W, T, st);
+                           L0.relu, save ? reinterpret_cast<__half*>(save[0]) : act[0], g.plane_elems, B, H, W, T, st);
   }
   if (rc) return rc;
   int cur = 0;
   for (int i = 1; i < nl - 1; ++i) {
     const Layer& L = h->layers[i];
+    const __half* a_in = in_buf(i, cur);
+    __half* a_out = out_buf(i, cur);
     if (h->precision == DEQSCI_PREC_FP32)
-      rc = conv_mid_fp32_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
+      rc = conv_mid_fp32_launch(a_in, a_out, g.plane_elems, L.w_cc, L.scale, L.bias, L.relu, g.NF, g.Hc,
                                 g.Wc, st);
     else if (bn && bn[i].running_mean) {      // a BatchNorm follows this conv (gamma / beta are NULL for affine=False)
       // train mode: raw conv + per-channel statistics, then batch-statistics BatchNorm (+ ReLU) in place
-      rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
+      rc = conv_hidden_2cta_launch(a_in, a_out, g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
                                    g.Wc, st, bn_stats);
       if (rc == DEQSCI_OK)
-        rc = bn_train_launch(act[cur ^ 1], g.plane_elems, bn_stats, num_sms(), bn_scale_shift, bn[i].gamma, bn[i].beta,
+        rc = bn_train_launch(a_out, g.plane_elems, bn_stats, num_sms(), bn_scale_shift, bn[i].gamma, bn[i].beta,
                              bn[i].running_mean, bn[i].running_var, momentum, eps, (long long)g.NF * g.Hc * g.Wc,
                              L.relu, st);
     } else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))
-      rc = conv_hidden_2cta_launch(act[cur], act[cur ^ 1], g.plane_elems, L.w_tc2, L.scale, L.bias, L.relu, g.NF,
-                                   g.Hc, g.Wc, st);
+      rc = conv_hidden_2cta_launch(a_in, a_out, g.plane_elems, L.w_tc2, L.scale, L.bias, relu_of(i, L.relu), g.NF,
+                                   g.Hc, g.Wc, st, nullptr, mask_of(i));
     else
-      rc = conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], act[cur ^ 1], g.plane_elems, L.w_tc,
+      rc = conv_mid_tc_launch(h->precision == DEQSCI_PREC_TC_SPLIT, a_in, a_out, g.plane_elems, L.w_tc,
                               L.scale, L.bias, L.relu, g.NF, g.Hc, g.Wc, st);
     if (rc) return rc;
     cur ^= 1;
   }
   const Layer& LL = h->layers[nl - 1];
+  const __half* a_last = save ? reinterpret_cast<const __half*>(save[nl - 2]) : act[cur];
   if (h->precision != DEQSCI_PREC_FP32 && tcl_supported(g.Wc))
-    return conv_last_tc_launch(LL.cout, act[cur], g.plane_elems, LL.w_tc2, LL.scale, LL.bias, LL.relu, g.NF, g.Hc,
+    return conv_last_tc_launch(LL.cout, a_last, g.plane_elems, LL.w_tc2, LL.scale, LL.bias, LL.relu, g.NF, g.Hc,
                                g.Wc, fuse_gap ? zprime_ws : z, zprime_planar, out, H, W, T, st);
   if (h->precision != DEQSCI_PREC_FP32)
-    return conv_tc_launch(h->kind == DEQSCI_NET_FFDNET ? 1 : 2, h->precision == DEQSCI_PREC_TC_SPLIT, act[cur], nullptr,
+    return conv_tc_launch(h->kind == DEQSCI_NET_FFDNET ? 1 : 2, h->precision == DEQSCI_PREC_TC_SPLIT, a_last, nullptr,
                           g.plane_elems, LL.w_tc, LL.scale, LL.bias, LL.relu, g.NF, g.Hc, g.Wc,
                           fuse_gap ? zprime_ws : z, out, H, W, T, st);
-  return conv_last_launch(h->kind, act[cur], g.plane_elems, LL.w_cc, LL.scale, LL.bias, LL.relu,
+  return conv_last_launch(h->kind, a_last, g.plane_elems, LL.w_cc, LL.scale, LL.bias, LL.relu,
                           fuse_gap ? zprime_ws : z, out, B, H, W, T, st);
 }
 
@@ -402,6 +422,29 @@ extern "C" int deqsci_iterate(const deqsci_denoiser* h, const float* z, const fl
                               const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
                               int B, int H, int W, int T, void* stream) {
   return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream);
+}
+
+extern "C" size_t deqsci_denoiser_activation_bytes(const deqsci_denoiser* h, int B, int H, int W, int T) {
+  Geometry g;
+  if (geometry(h, B, H, W, T, &g) != DEQSCI_OK) return 0;
+  return g.act_bytes;
+}
+
+extern "C" int deqsci_iterate_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                                   const float* phi_sum, float sigma, float* out, void* workspace,
+                                   size_t workspace_bytes, void* const* acts_host, int B, int H, int W, int T,
+                                   void* stream) {
+  DEQSCI_CHECK_ARG(acts_host != nullptr, "iterate_save: null activation table");
+  return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream, nullptr,
+                   0.f, 0.f, acts_host, nullptr);
+}
+
+extern "C" int deqsci_denoise_residual_masked(const deqsci_denoiser* h_adjoint, const float* vin, float* out,
+                                              void* workspace, size_t workspace_bytes, const void* const* masks_host,
+                                              int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(masks_host != nullptr, "denoise_residual_masked: null mask table");
+  return run_stack(h_adjoint, false, vin, nullptr, nullptr, nullptr, 0.f, out, workspace, workspace_bytes, B, H, W, T,
+                   stream, nullptr, 0.f, 0.f, nullptr, masks_host);
 }
 
 extern "C" int deqsci_iterate_train(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,

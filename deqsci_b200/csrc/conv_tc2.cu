@@ -119,6 +119,8 @@ struct Params {
   int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
   __half* dbg_out_hi;
   __half* dbg_out_lo;
+  const __half* mask;         // relu == 2: output (pixel, channel) is kept where this hi plane [NF,Hc,Wc,64] is > 0, else
+                              // zeroed: the ReLU derivative of a saved forward activation (adjoint / VJP stacks)
 };
 
 struct Strip { int nf, h0, w0; bool real; };
@@ -286,6 +288,21 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
       for (int j = 0; j < p.strip_rows; ++j) {
         const int h = s.h0 + j;
         const bool px_valid = col_valid && h < p.Hc;
+        // mask words of this thread's pixel and 32 channels, fetched before the accumulator wait
+        uint32_t mkw[16];
+        if (p.relu == 2) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) mkw[q] = 0u;
+          if (px_valid) {
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask + (((long long)s.nf * p.Hc + h) * p.Wc + (s.w0 + quarter * 32 + lane)) * 64 + half * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t4 = __ldg(mp + q);
+              mkw[4 * q] = t4.x; mkw[4 * q + 1] = t4.y; mkw[4 * q + 2] = t4.z; mkw[4 * q + 3] = t4.w;
+            }
+          }
+        }
         mbar_wait(bar_tfull(buf), tphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
@@ -307,7 +324,12 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
               float a = fmaf(__uint_as_float(c1[i + u]) + __uint_as_float(c2[i + u]), kLoInvScale,
                              __uint_as_float(acc[i + u]));
               a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
-              v[u] = p.relu ? fmaxf(a, 0.f) : a;
+              if (p.relu == 2) {         // gate by the saved activation's sign (fp16 hi half != +0)
+                const uint32_t mbits = (mkw[part * 8 + (i >> 1)] >> (16 * u)) & 0x7fffu;
+                v[u] = mbits ? a : 0.f;
+              } else {
+                v[u] = p.relu ? fmaxf(a, 0.f) : a;
+              }
               if (STATS && px_valid) {
                 st_sum[part * 16 + i + u] += v[u];
                 st_sq[part * 16 + i + u] = fmaf(v[u], v[u], st_sq[part * 16 + i + u]);
@@ -439,9 +461,11 @@ bool tc2_supported(int Hc, int Wc) {
 
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
-                            cudaStream_t st, double* stats) {
+                            cudaStream_t st, double* stats, const __half* mask) {
   tc2::Params p;
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
+  p.mask = mask;
+  if (relu == 2 && !mask) { set_error("conv_hidden_2cta_launch: masked layer without a mask plane"); return DEQSCI_ERR_INVALID; }
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tc2::kTileM - 1) / tc2::kTileM;
   const int pairs_hw = num_sms() / 2;

@@ -47,6 +47,7 @@ struct Params {
   int NF, Hc, Wc;
   int tiles_x, strips_y, strip_rows;
   long long n_items;
+  const __half* mask;      // relu == 2: keep (pixel, channel) where this hi plane [NF,Hc,Wc,64] is > 0 (see conv_tc2.cu)
 };
 struct Item { int nf, h0, w0, ntiles; };
 
@@ -184,6 +185,21 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_map,
       const Item it = decode(p, item);
       for (int j = 0; j < it.ntiles; ++j) {
         const int h = it.h0 + j;
+        uint32_t mkw[16];
+        if (p.relu == 2) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) mkw[q] = 0u;
+          const int wpx = it.w0 + quarter * 32 + lane;
+          if (wpx < p.Wc && h < p.Hc) {
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask + (((long long)it.nf * p.Hc + h) * p.Wc + wpx) * 64 + half * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t4 = __ldg(mp + q);
+              mkw[4 * q] = t4.x; mkw[4 * q + 1] = t4.y; mkw[4 * q + 2] = t4.z; mkw[4 * q + 3] = t4.w;
+            }
+          }
+        }
         mbar_wait(bar_tfull(buf), tphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
@@ -205,7 +221,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap in_map,
             for (int u = 0; u < 2; ++u) {
               float a = __uint_as_float(acc[i + u]);
               if (AFFINE) a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
-              v[u] = p.relu ? fmaxf(a, 0.f) : a;
+              if (p.relu == 2) {
+                const uint32_t mbits = (mkw[part * 8 + (i >> 1)] >> (16 * u)) & 0x7fffu;
+                v[u] = mbits ? a : 0.f;
+              } else {
+                v[u] = p.relu ? fmaxf(a, 0.f) : a;
+              }
             }
             split_f16x2(v[0], v[1], hi_pk[part * 8 + (i >> 1)], lo_pk[part * 8 + (i >> 1)]);
           }
@@ -284,9 +305,11 @@ bool tcf_supported(int Wc) {
 // planes_in: [NF,Hc,Wc,16] fp16, K-packed rows (gap_prep_kernel); act_out: [2][NF,Hc,Wc,64] fp16
 int conv_first_tc_launch(const __half* planes_in, long long in_plane_elems, __half* act_out, long long plane_elems,
                          const uint8_t* wimg, const float* scale, const float* bias, int relu, int NF, int Hc,
-                         int Wc, cudaStream_t st) {
+                         int Wc, cudaStream_t st, const __half* mask) {
   tcf::Params p;
   p.wimg = wimg; p.scale = scale; p.bias = bias; p.relu = relu;
+  p.mask = mask;
+  if (relu == 2 && !mask) { set_error("conv_first_tc_launch: masked layer without a mask plane"); return DEQSCI_ERR_INVALID; }
   p.NF = NF; p.Hc = Hc; p.Wc = Wc;
   p.tiles_x = (Wc + tcf::kTileM - 1) / tcf::kTileM;
   const int R = pick_strip_rows_balanced(NF, p.tiles_x, Hc, false, 2 * num_sms(), 1, 1, 2);

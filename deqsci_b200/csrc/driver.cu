@@ -80,7 +80,8 @@ Layout layout(const deqsci_denoiser* h, int B, int H, int W, int T, int m) {
   L.alpha_floats = align_up_sz((size_t)B * m, 64);
   L.scratch_floats = align_up_sz(deqsci_anderson_scratch_floats(B, m, (long long)N), 64);
   L.floats_total = L.hist_floats + L.gram_floats + L.alpha_floats + L.scratch_floats + 64 /*res*/ +
-                   (size_t)kMaxBnLayers * 2 * kHidden /*running-statistics snapshot*/;
+                   (size_t)kMaxBnLayers * 2 * kHidden /*running-statistics snapshot*/ +
+                   align_up_sz((size_t)B * N, 64) /*one cube of scratch: the masked-adjoint map's intermediate*/;
   L.den_bytes = h ? deqsci_denoiser_workspace_bytes(h, B, H, W, T) : 0;
   L.total_bytes = 1024 + align_up_sz(L.floats_total * sizeof(float), 1024) + L.den_bytes;
   return L;
@@ -104,11 +105,13 @@ namespace {
 //   h, bn            : f = the iterate map in train mode (deqsci_iterate_train)
 //   h == nullptr     : f(v) = gap_vjp(v) + adjoint_grad, the backward fixed-point map of tag 'ffdnet'
 //                      (solvers/new_equilibrium_utils_yaping.py:274-277); y is unused
+//   h, masks         : f(v) = gap_vjp(v - J_D^T v) + adjoint_grad, the same map for tag 'denoiser': h is the ADJOINT
+//                      plan (transposed, flipped weights in reverse order) and masks the saved forward activations
 int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, const float* phi_sum,
                      const float* x0, float* out, const deqsci_solver_opts* o, const deqsci_bn_params* bn,
                      float momentum, float eps, const float* adjoint_grad, void* workspace,
                      size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
-                     void* stream) {
+                     void* stream, const void* const* masks = nullptr) {
   DEQSCI_CHECK_ARG((h || adjoint_grad) && (y || adjoint_grad) && phi && phi_sum && out && o && workspace && result,
                    "reconstruct: null pointer");
   DEQSCI_CHECK_ARG(o->m >= 2 && o->m <= 8, "reconstruct: m=%d unsupported (2..8)", o->m);
@@ -135,6 +138,7 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
   float* scratch = alpha + L.alpha_floats;
   float* res_dev = scratch + L.scratch_floats;
   float* bn_backup = res_dev + 64;
+  float* tmp_cube = bn_backup + (size_t)kMaxBnLayers * 2 * kHidden;
   const int n_layers = denoiser_num_layers(h);
   void* den_ws = base + align_up_sz(L.floats_total * sizeof(float), 1024);
   const size_t slot = (size_t)B * N;
@@ -149,6 +153,11 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
     sigma_prev = sigma;
     sigma = sigma * o->sigma_decay;
     ++calls;
+    if (masks) {
+      const int rc_m = deqsci_denoise_residual_masked(h, zin, tmp_cube, den_ws, L.den_bytes, masks, B, H, W, T, stream);
+      if (rc_m) return rc_m;
+      return deqsci_gap_vjp(tmp_cube, phi, phi_sum, adjoint_grad, zout, B, H, W, T, stream);
+    }
     if (!h) return deqsci_gap_vjp(zin, phi, phi_sum, adjoint_grad, zout, B, H, W, T, stream);
     if (bn)
       return deqsci_iterate_train(h, zin, y, phi, phi_sum, sigma_prev, zout, den_ws, L.den_bytes, bn, momentum, eps, B,
@@ -257,4 +266,16 @@ extern "C" int deqsci_adjoint_solve(const float* grad, const float* phi, const f
   opts.final_call = 0;                 // the reference returns the solver's iterate, not one more evaluation
   return anderson_loop(nullptr, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
                           workspace_bytes, result, B, H, W, T, stream);
+}
+
+extern "C" int deqsci_adjoint_solve_denoiser(const deqsci_denoiser* h_adjoint, const void* const* masks_host,
+                                             const float* grad, const float* phi, const float* phi_sum, float* out,
+                                             const deqsci_solver_opts* o, void* workspace, size_t workspace_bytes,
+                                             deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
+  DEQSCI_CHECK_ARG(h_adjoint != nullptr && masks_host != nullptr && grad != nullptr && o != nullptr,
+                   "adjoint_solve_denoiser: null pointer");
+  deqsci_solver_opts opts = *o;
+  opts.final_call = 0;
+  return anderson_loop(h_adjoint, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
+                       workspace_bytes, result, B, H, W, T, stream, masks_host);
 }

@@ -147,6 +147,72 @@ class NativeDenoiser:
                                        _stream(z)), "deqsci_iterate")
         return out
 
+    # ---- backward of a conv / ReLU stack on the same kernels (tag 'denoiser', DE-GAP-CNN) ------------------
+    def iterate_save(self, z, y, phi, phi_sum, sigma=0.0):
+        """One call of the iterate map that also keeps every hidden activation (deqsci_iterate_save).  Returns
+        (out, acts): acts[i] = output planes of conv layer i, fp16 [2, B*T, Hc, Wc, 64] (hi plane, lo plane)."""
+        z, y = _req(z, "z", 4), _req(y, "y", 3)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
+        self._check_dev(z)
+        B, H, W, T = (int(s) for s in z.shape)
+        out = torch.empty_like(z)
+        ws = self._workspace(B, H, W, T)
+        nbytes = lib().deqsci_denoiser_activation_bytes(self._h, B, H, W, T)
+        acts = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(self.num_layers - 1)]
+        ptrs = (ctypes.c_void_p * len(acts))(*[a.data_ptr() for a in acts])
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_iterate_save(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                            float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), ptrs, B, H, W, T,
+                                            _stream(z)), "deqsci_iterate_save")
+        return out, acts
+
+    def _mask_table(self, masks):
+        if len(masks) != self.num_layers - 1:
+            raise DeqsciError("%d mask planes for %d gated layers" % (len(masks), self.num_layers - 1))
+        for m in masks:
+            self._check_dev(m)
+        return (ctypes.c_void_p * len(masks))(*[m.data_ptr() for m in masks])
+
+    def denoise_residual_masked(self, v, masks, out=None):
+        """On an ADJOINT plan: out = v - J_D^T v, the ReLUs of the stack replaced by the sign of the saved forward
+        activations `masks` (masks[i] gates adjoint layer i; deqsci_denoise_residual_masked)."""
+        v = _req(v, "v", 4)
+        self._check_dev(v)
+        B, H, W, T = (int(s) for s in v.shape)
+        if out is None:
+            out = torch.empty_like(v)
+        ws = self._workspace(B, H, W, T)
+        tab = self._mask_table(masks)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_denoise_residual_masked(self._h, v.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                       tab, B, H, W, T, _stream(v)), "deqsci_denoise_residual_masked")
+        return out
+
+    def adjoint_solve(self, grad, phi, phi_sum, masks, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5):
+        """On an ADJOINT plan: the implicit-differentiation hook's backward solve for tag 'denoiser' in ONE C-ABI
+        call (deqsci_adjoint_solve_denoiser): andersonexp on g -> gap_vjp(g - J_D^T g) + grad, started at grad
+        (reference solvers/new_equilibrium_utils_yaping.py:274-277).  Returns (g, backward_res)."""
+        grad = _req(grad, "grad", 4)
+        phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), grad), _bcast_phi(_req(phi_sum, "Phi_sum", 3), grad)
+        self._check_dev(grad)
+        B, H, W, T = (int(s) for s in grad.shape)
+        need = lib().deqsci_reconstruct_workspace_bytes(self._h, B, H, W, T, int(m))
+        if need == 0:
+            raise DeqsciError("adjoint_solve: unsupported shape or history m=%d" % m)
+        if self._rws is None or self._rws.numel() < need:
+            self._rws = None
+            self._rws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty_like(grad)
+        opts = _lib.SolverOpts(int(m), float(lam), float(beta), int(max_iter), float(tol), 0.0, 1.0, 0, 0, 1e-5)
+        res = _lib.SolverResult()
+        tab = self._mask_table(masks)
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_adjoint_solve_denoiser(self._h, tab, grad.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                                      out.data_ptr(), ctypes.byref(opts), self._rws.data_ptr(),
+                                                      self._rws.numel(), ctypes.byref(res), B, H, W, T, _stream(grad)),
+                  "deqsci_adjoint_solve_denoiser")
+        return out, float(res.residual)
+
     def _bn_table(self, bn_modules):
         if len(bn_modules) != self.num_layers:
             raise DeqsciError("%d BatchNorm slots for %d conv layers" % (len(bn_modules), self.num_layers))

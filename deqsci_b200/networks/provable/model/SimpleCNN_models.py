@@ -66,6 +66,42 @@ class DnCNN(nn.Module, NativePlanCache):
                 and os.environ.get("DEQSCI_TC_PAIR", "1") != "0"      # the train path lives in the CTA-pair kernel
                 and W > 64)
 
+    # -- the stack's VJP on the same kernels (backward solve of the implicit-differentiation hook) ---------
+    def native_adjoint_ok(self, z):
+        """Plain conv / ReLU stack (no BatchNorm, no spectral-norm hook: J_D^T is then the same stack with transposed,
+        flipped weights and the ReLUs replaced by the saved activations' signs), on the CTA-pair / first-layer
+        tensor-core kernels: cube [B,H,W,T] wider than 64 pixels, precision tc_split."""
+        from ....native import default_precision
+        convs = [m for m in self.dncnn if isinstance(m, nn.Conv2d)]
+        return (z.is_cuda and self.channels == 1 and self._stateless_in_train_mode() and len(convs) >= 3
+                and all(c.bias is None and tuple(c.weight.shape[2:]) == (3, 3) for c in convs)
+                and (getattr(self, "precision", None) or default_precision()) == "tc_split"
+                and os.environ.get("DEQSCI_TC_PAIR", "1") != "0" and os.environ.get("DEQSCI_TC_FIRST", "1") != "0"
+                and int(z.shape[2]) > 64)
+
+    def native_adjoint_plan(self, device):
+        """NativeDenoiser built from the layers in reverse order with W'[c][o][ky][kx] = W[o][c][2-ky][2-kx]; refreshed
+        on the device (no host copy) when the weights have changed since it was packed."""
+        from ....native import NativeDenoiser
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        ws = [m.weight for m in self.dncnn if isinstance(m, nn.Conv2d)]
+        sig = tuple((id(w), w._version, w.data_ptr()) for w in ws)
+        with torch.no_grad():
+            adj = [w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous() for w in reversed(ws)]
+        hit = self.__dict__.get("_native_adjoint")
+        if hit is not None and hit[1].device == device and hit[1].num_layers == len(adj):
+            if hit[0] != sig:
+                hit[1].update_weights(adj)
+                self.__dict__["_native_adjoint"] = (sig, hit[1])
+            return self.__dict__["_native_adjoint"][1]
+        layers = [{"weight": a.float().cpu(), "scale": None, "bias": None, "relu": i < len(adj) - 1}
+                  for i, a in enumerate(adj)]
+        plan = NativeDenoiser("dncnn", layers, getattr(self, "precision", None), device)
+        self.__dict__["_native_adjoint"] = (sig, plan)
+        return plan
+
     def _stateless_in_train_mode(self):
         return all(isinstance(m, (nn.Conv2d, nn.ReLU)) for m in self.dncnn)
 

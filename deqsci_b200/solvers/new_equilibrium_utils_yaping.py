@@ -357,7 +357,23 @@ class DEQFixedPoint(nn.Module):
         native_vjp = (getattr(getattr(self.f, "nonlinear_op", None), "tag", None) == 'ffdnet' and z.is_cuda
                       and getattr(self.f, "A", None) is cg_utils.A_torch_ and getattr(self.f, "At", None) is cg_utils.At_torch_)
         z0 = z.clone().detach().requires_grad_()
-        if native_vjp:
+        # tag 'denoiser' with a plain conv / ReLU stack: J_f^T v = P (v - J_D^T v), and J_D^T is the SAME conv kernels on
+        # transposed, flipped weights gated by the signs of the activations of f(z0) -- no autograd graph, no cuDNN
+        # dgrad per solver iteration
+        import os
+        op_ = getattr(self.f, "nonlinear_op", None)
+        kw_ok = (self.solver is andersonexp and os.environ.get("DEQSCI_DRIVER", "1") != "0"
+                 and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"} and self.kwargs.get("max_iter", 50) >= 2)
+        native_den = (not native_vjp and getattr(op_, "tag", None) == 'denoiser' and z.is_cuda and kw_ok
+                      and getattr(self.f, "A", None) is cg_utils.A_torch_ and getattr(self.f, "At", None) is cg_utils.At_torch_
+                      and getattr(op_, "native_adjoint_ok", lambda t: False)(z) and z.dtype == torch.float32)
+        acts = None
+        if native_den:
+            with torch.no_grad():
+                # the reference's second call f(z0): its values are not needed, its activations are
+                _, acts = op_.native_plan(z.device).iterate_save(z0.detach(), x, Phi, Phi_sum, 0.0)
+            f0 = None
+        elif native_vjp:
             # the reference's second call f(z0) only feeds autograd.grad; its side effects (sigma step,
             # BatchNorm running statistics) are kept, its graph is not needed
             with torch.no_grad():
@@ -368,6 +384,11 @@ class DEQFixedPoint(nn.Module):
 
         def backward_hook(grad):
             import os
+            if native_den and grad.dtype == torch.float32:
+                # adjoint layer i is gated by the activation of forward layer L-2-i (hi plane = start of the buffer)
+                g, self.backward_res = op_.native_adjoint_plan(z.device).adjoint_solve(
+                    grad.contiguous(), Phi, Phi_sum, masks=list(reversed(acts)), **self.kwargs)
+                return g
             if (native_vjp and self.solver is andersonexp and os.environ.get("DEQSCI_DRIVER", "1") != "0"
                     and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"}
                     and self.kwargs.get("max_iter", 50) >= 2 and grad.dtype == torch.float32):

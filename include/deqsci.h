@@ -246,6 +246,32 @@ int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_s
                          const deqsci_solver_opts* opts, void* workspace, size_t workspace_bytes,
                          deqsci_solver_result* result, int B, int H, int W, int T, void* stream);
 
+/* The implicit-differentiation hook for tag 'denoiser' (DE-GAP-CNN, solvers/new_equilibrium_utils_yaping.py:271-277):
+ * the reference evaluates f0 = f(z0) with a graph and runs andersonexp on g -> autograd.grad(f0, z0, g) + grad, i.e.
+ * one full backward pass of the conv stack per solver iteration.  Here:
+ *  - deqsci_iterate_save is deqsci_iterate that also keeps every hidden activation: acts_host[i]
+ *    (i = 0 .. num_layers-2, device buffers of deqsci_denoiser_activation_bytes() each) receives the output planes of
+ *    conv layer i ([hi plane | lo plane], channels-last [B*T,Hc,Wc,64] fp16);
+ *  - the VJP of the conv / ReLU stack is the SAME kernels run on an ADJOINT plan -- created with
+ *    deqsci_denoiser_create from the layers in reverse order, weights transposed and flipped
+ *    (W'[c][o][ky][kx] = W[o][c][2-ky][2-kx]) -- whose ReLUs are replaced by the sign of the saved activations:
+ *    masks_host[i] gates the output of adjoint layer i (= acts of forward layer num_layers-2-i).
+ *    deqsci_denoise_residual_masked computes out = v - J_D^T v;
+ *  - deqsci_adjoint_solve_denoiser is the whole backward solve: andersonexp on g -> gap_vjp(g - J_D^T g) + grad
+ *    (workspace: deqsci_reconstruct_workspace_bytes(h_adjoint, ...)).
+ * Plain conv / ReLU stacks (no folded BatchNorm), precision TC_SPLIT, conv images wider than 64 pixels. */
+size_t deqsci_denoiser_activation_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
+int deqsci_iterate_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                        const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
+                        void* const* acts_host, int B, int H, int W, int T, void* stream);
+int deqsci_denoise_residual_masked(const deqsci_denoiser* h_adjoint, const float* vin, float* out,
+                                   void* workspace, size_t workspace_bytes, const void* const* masks_host,
+                                   int B, int H, int W, int T, void* stream);
+int deqsci_adjoint_solve_denoiser(const deqsci_denoiser* h_adjoint, const void* const* masks_host,
+                                  const float* grad, const float* phi, const float* phi_sum, float* out,
+                                  const deqsci_solver_opts* opts, void* workspace, size_t workspace_bytes,
+                                  deqsci_solver_result* result, int B, int H, int W, int T, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Gradient exchange of the training step fused with the optimizer (csrc/optim.cu).  The reference has no
  * distributed backend; this is the one exchange step data-parallel training adds between loss.backward() and

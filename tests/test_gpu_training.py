@@ -152,10 +152,12 @@ def test_train_driver_equals_python_loop(train_wide_vectors, d, monkeypatch):
                        deq.backward_res)
     a, b = out["1"], out["0"]
     assert torch.equal(a[0], b[0])
-    # gradients come out of cuDNN's backward kernels (atomics): equal up to their run-to-run noise
+    # gradients come out of cuDNN's backward kernels (atomics): equal up to their run-to-run noise.  SimpleCNN: with the
+    # driver the backward solve's VJPs run on the native masked-adjoint stack, without it on cuDNN dgrads -- two fp32
+    # implementations of the same 12-iteration solve (both within 1e-3 of the reference, test above)
     assert a[1].keys() == b[1].keys()
     for k in a[1]:
-        assert rel_l2(a[1][k].cpu().numpy(), b[1][k].cpu().numpy()) <= 1e-5, k
+        assert rel_l2(a[1][k].cpu().numpy(), b[1][k].cpu().numpy()) <= (2e-4 if d == "SimpleCNN" else 1e-5), k
     assert all(torch.equal(a[2][k], b[2][k]) for k in a[2])
     assert a[3] == b[3]
     assert a[4] == b[4]
@@ -226,3 +228,61 @@ def test_fused_allreduce_adam_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29653",
                         os.path.join(ROOT, "scripts", "fused_adam_check.py")], capture_output=True, text=True, timeout=600)
     assert "FUSED_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_masked_adjoint_vjp_vs_autograd(train_wide_vectors):
+    """Tag 'denoiser': the VJP of the iterate map on the native kernels -- the conv stack with transposed, flipped weights
+    gated by the saved activations' signs (deqsci_iterate_save / deqsci_denoise_residual_masked), then the GAP
+    projector -- against torch.autograd.grad through the PyTorch evaluation of the same map
+    (reference solvers/new_equilibrium_utils_yaping.py:271-277)."""
+    from test_gpu_parity import build_solver
+    from deqsci_b200 import ops
+    from deqsci_b200.utils.cg_utils import Phi_sum_
+    dev = torch.device("cuda", 0)
+    v = train_wide_vectors
+    solver = build_solver("SimpleCNN", dev)
+    solver.train()
+    op = solver.nonlinear_op
+    gt, Phi, y = (torch.from_numpy(v[k]).to(dev) for k in ("gt", "Phi", "y"))
+    Ps = Phi_sum_(Phi)
+    g = torch.Generator().manual_seed(11)
+    z0 = (gt + 0.05 * torch.randn(gt.shape, generator=g).to(dev)).requires_grad_()
+    vec = torch.randn(gt.shape, generator=g).to(dev)
+    assert op.native_adjoint_ok(z0)
+    f0 = solver._autograd_forward(z0, y, Phi, Ps)
+    want = torch.autograd.grad(f0, z0, vec)[0]
+    with torch.no_grad():
+        out, acts = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)
+        assert rel_l2(out.cpu().numpy(), f0.detach().cpu().numpy()) <= 2e-5          # same forward values
+        adj = op.native_adjoint_plan(dev)
+        got = ops.gap_vjp(adj.denoise_residual_masked(vec, list(reversed(acts))), Phi, Ps)
+    # against autograd: the ReLU masks come from two fp32 evaluations of the forward pass (cuDNN vs the native stack);
+    # pre-activations within ~1e-6 of zero flip, each flip is an O(1) error on its path: ~2e-4 overall
+    assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) <= 5e-4
+    # against the same chain in PyTorch with the SAME masks (the saved native activations): arithmetic only
+    import torch.nn.functional as F
+
+    def torch_vjp(acts_):
+        B, H, W, T = vec.shape
+        convs = [m for m in op.dncnn if isinstance(m, torch.nn.Conv2d)]
+        u = vec.permute(0, 3, 1, 2).reshape(B * T, 1, H, W)
+        for i in range(len(convs) - 1, -1, -1):
+            u = F.conv_transpose2d(u, convs[i].weight, padding=1)
+            if i > 0:
+                hi = acts_[i - 1].view(torch.float16).view(2, B * T, H, W, 64)[0]
+                u = u * (hi > 0).permute(0, 3, 1, 2).float()
+        r = vec - u.view(B, T, H, W).permute(0, 2, 3, 1)
+        return ops.gap_vjp(r.contiguous(), Phi, Ps)
+
+    with torch.no_grad():
+        assert rel_l2(got.cpu().numpy(), torch_vjp(acts).cpu().numpy()) <= 2e-5
+    # after an in-place weight update the adjoint plan is refreshed on the device and still matches
+    with torch.no_grad():
+        for p_ in op.parameters():
+            p_.mul_(1.02)
+        _, acts1 = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)
+        adj1 = op.native_adjoint_plan(dev)
+        assert adj1 is adj
+        got1 = ops.gap_vjp(adj1.denoise_residual_masked(vec, list(reversed(acts1))), Phi, Ps)
+        assert rel_l2(got1.cpu().numpy(), torch_vjp(acts1).cpu().numpy()) <= 2e-5
+    assert rel_l2(got1.cpu().numpy(), got.cpu().numpy()) > 1e-3
