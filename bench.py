@@ -477,6 +477,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             side["DE-GAP-" + {"SimpleCNN": "CNN", "RealSN_SimpleCNN": "RSN-CNN"}[dn]] = {
                 "recon_per_s": B * 3 / (ms_side / 1e3), "and_maxiters": 100, "batch": B}
             del dq
+        # config 5 with the DnCNN-style denoiser: its backward solve runs on the masked-adjoint conv stack
+        ts = train_step_bench(dev, rank, world, steps=3, warmup=1, batch=args.train_batch, denoiser="SimpleCNN", data=args.data)
+        side["DE-GAP-CNN train_step"] = {"ms_per_step": ts["ms_per_step"], "batch": args.train_batch, "and_maxiters": 100,
+                                         "backward_res": ts["backward_res"]}
         extras["side"] = side
         try:
             extras["gpu_eager_baseline"] = {

@@ -72,7 +72,7 @@ SIGNATURES = {
     "deqsci_iterate_save": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int,
                                     c_int, _P]),
     "deqsci_denoise_residual_masked": (c_int, [_P, _P, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int, c_int, _P]),
-    "deqsci_adjoint_solve_denoiser": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t,
+    "deqsci_adjoint_solve_denoiser": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, POINTER(SolverOpts), c_float, _P, c_size_t,
                                               POINTER(SolverResult), c_int, c_int, c_int, c_int, _P]),
     "deqsci_comm_bytes": (c_size_t, [c_longlong]),
     "deqsci_comm_alloc": (c_int, [c_longlong, POINTER(_P), _P]),

@@ -67,6 +67,11 @@ void release_ring(ResidualRing* r) {
   g_free_rings.push_back(r);
 }
 
+__global__ void scale_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, float s, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i] * s;
+}
+
 struct Layout {
   size_t hist_floats, gram_floats, alpha_floats, scratch_floats, floats_total;
   size_t den_bytes, total_bytes;
@@ -111,7 +116,7 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
                      const float* x0, float* out, const deqsci_solver_opts* o, const deqsci_bn_params* bn,
                      float momentum, float eps, const float* adjoint_grad, void* workspace,
                      size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
-                     void* stream, const void* const* masks = nullptr) {
+                     void* stream, const void* const* masks = nullptr, float vjp_scale = 1.f) {
   DEQSCI_CHECK_ARG((h || adjoint_grad) && (y || adjoint_grad) && phi && phi_sum && out && o && workspace && result,
                    "reconstruct: null pointer");
   DEQSCI_CHECK_ARG(o->m >= 2 && o->m <= 8, "reconstruct: m=%d unsupported (2..8)", o->m);
@@ -154,8 +159,20 @@ int anderson_loop(const deqsci_denoiser* h, const float* y, const float* phi, co
     sigma = sigma * o->sigma_decay;
     ++calls;
     if (masks) {
-      const int rc_m = deqsci_denoise_residual_masked(h, zin, tmp_cube, den_ws, L.den_bytes, masks, B, H, W, T, stream);
+      // J_D^T is linear: evaluate it on vjp_scale * v (a power of two chosen by the caller so the operand planes sit
+      // in fp16's normal range -- loss gradients are ~1e-7 per element at full size, below fp16's subnormal step) and
+      // scale back; the Anderson state itself keeps the reference's magnitudes (its lam * I term is scale-dependent)
+      const float* vin = zin;
+      if (vjp_scale != 1.f) {
+        scale_copy_kernel<<<(unsigned)std::min<long long>(((long long)slot + 1023) / 1024, 148 * 8), 256, 0, st>>>(
+            zout, zin, vjp_scale, (long long)slot);
+        vin = zout;                                   // zout is free until the projector writes it below
+      }
+      const int rc_m = deqsci_denoise_residual_masked(h, vin, tmp_cube, den_ws, L.den_bytes, masks, B, H, W, T, stream);
       if (rc_m) return rc_m;
+      if (vjp_scale != 1.f)
+        scale_copy_kernel<<<(unsigned)std::min<long long>(((long long)slot + 1023) / 1024, 148 * 8), 256, 0, st>>>(
+            tmp_cube, tmp_cube, 1.f / vjp_scale, (long long)slot);
       return deqsci_gap_vjp(tmp_cube, phi, phi_sum, adjoint_grad, zout, B, H, W, T, stream);
     }
     if (!h) return deqsci_gap_vjp(zin, phi, phi_sum, adjoint_grad, zout, B, H, W, T, stream);
@@ -270,12 +287,14 @@ extern "C" int deqsci_adjoint_solve(const float* grad, const float* phi, const f
 
 extern "C" int deqsci_adjoint_solve_denoiser(const deqsci_denoiser* h_adjoint, const void* const* masks_host,
                                              const float* grad, const float* phi, const float* phi_sum, float* out,
-                                             const deqsci_solver_opts* o, void* workspace, size_t workspace_bytes,
-                                             deqsci_solver_result* result, int B, int H, int W, int T, void* stream) {
+                                             const deqsci_solver_opts* o, float vjp_scale, void* workspace,
+                                             size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W,
+                                             int T, void* stream) {
   DEQSCI_CHECK_ARG(h_adjoint != nullptr && masks_host != nullptr && grad != nullptr && o != nullptr,
                    "adjoint_solve_denoiser: null pointer");
+  DEQSCI_CHECK_ARG(vjp_scale > 0.f && vjp_scale < 3.0e38f, "adjoint_solve_denoiser: vjp_scale must be a positive finite number");
   deqsci_solver_opts opts = *o;
   opts.final_call = 0;
   return anderson_loop(h_adjoint, nullptr, phi, phi_sum, /*x0=*/grad, out, &opts, nullptr, 0.f, 0.f, grad, workspace,
-                       workspace_bytes, result, B, H, W, T, stream, masks_host);
+                       workspace_bytes, result, B, H, W, T, stream, masks_host, vjp_scale);
 }

@@ -188,11 +188,17 @@ class NativeDenoiser:
                                                        tab, B, H, W, T, _stream(v)), "deqsci_denoise_residual_masked")
         return out
 
-    def adjoint_solve(self, grad, phi, phi_sum, masks, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5):
+    def adjoint_solve(self, grad, phi, phi_sum, masks, m=5, lam=1e-4, beta=1.0, max_iter=50, tol=1e-5, vjp_scale=None):
         """On an ADJOINT plan: the implicit-differentiation hook's backward solve for tag 'denoiser' in ONE C-ABI
         call (deqsci_adjoint_solve_denoiser): andersonexp on g -> gap_vjp(g - J_D^T g) + grad, started at grad
-        (reference solvers/new_equilibrium_utils_yaping.py:274-277).  Returns (g, backward_res)."""
+        (reference solvers/new_equilibrium_utils_yaping.py:274-277).  Returns (g, backward_res).
+        vjp_scale (default: the power of two that brings max|grad| into [1, 2), one device sync): the conv stack is
+        evaluated on vjp_scale * g and the result scaled back (fp16 operand planes; see include/deqsci.h)."""
         grad = _req(grad, "grad", 4)
+        if vjp_scale is None:
+            gmax = float(grad.abs().max())
+            vjp_scale = 2.0 ** (-np.floor(np.log2(gmax))) if np.isfinite(gmax) and gmax > 0 else 1.0
+            vjp_scale = float(min(max(vjp_scale, 2.0 ** -60), 2.0 ** 60))
         phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), grad), _bcast_phi(_req(phi_sum, "Phi_sum", 3), grad)
         self._check_dev(grad)
         B, H, W, T = (int(s) for s in grad.shape)
@@ -208,8 +214,9 @@ class NativeDenoiser:
         tab = self._mask_table(masks)
         with torch.cuda.device(self.device):
             check(lib().deqsci_adjoint_solve_denoiser(self._h, tab, grad.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
-                                                      out.data_ptr(), ctypes.byref(opts), self._rws.data_ptr(),
-                                                      self._rws.numel(), ctypes.byref(res), B, H, W, T, _stream(grad)),
+                                                      out.data_ptr(), ctypes.byref(opts), float(vjp_scale),
+                                                      self._rws.data_ptr(), self._rws.numel(), ctypes.byref(res),
+                                                      B, H, W, T, _stream(grad)),
                   "deqsci_adjoint_solve_denoiser")
         return out, float(res.residual)
 

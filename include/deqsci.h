@@ -258,7 +258,9 @@ int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_s
  *    masks_host[i] gates the output of adjoint layer i (= acts of forward layer num_layers-2-i).
  *    deqsci_denoise_residual_masked computes out = v - J_D^T v;
  *  - deqsci_adjoint_solve_denoiser is the whole backward solve: andersonexp on g -> gap_vjp(g - J_D^T g) + grad
- *    (workspace: deqsci_reconstruct_workspace_bytes(h_adjoint, ...)).
+ *    (workspace: deqsci_reconstruct_workspace_bytes(h_adjoint, ...)).  vjp_scale: a power of two (1 = none); J_D^T is
+ *    evaluated on vjp_scale * g and scaled back, so that loss gradients of ~1e-7 per element sit in fp16's normal
+ *    range inside the conv kernels; the solver state keeps its own magnitudes (lam * I is scale-dependent).
  * Plain conv / ReLU stacks (no folded BatchNorm), precision TC_SPLIT, conv images wider than 64 pixels. */
 size_t deqsci_denoiser_activation_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
 int deqsci_iterate_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
@@ -269,8 +271,9 @@ int deqsci_denoise_residual_masked(const deqsci_denoiser* h_adjoint, const float
                                    int B, int H, int W, int T, void* stream);
 int deqsci_adjoint_solve_denoiser(const deqsci_denoiser* h_adjoint, const void* const* masks_host,
                                   const float* grad, const float* phi, const float* phi_sum, float* out,
-                                  const deqsci_solver_opts* opts, void* workspace, size_t workspace_bytes,
-                                  deqsci_solver_result* result, int B, int H, int W, int T, void* stream);
+                                  const deqsci_solver_opts* opts, float vjp_scale, void* workspace,
+                                  size_t workspace_bytes, deqsci_solver_result* result, int B, int H, int W, int T,
+                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Gradient exchange of the training step fused with the optimizer (csrc/optim.cu).  The reference has no
