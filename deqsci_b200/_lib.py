@@ -31,6 +31,10 @@ class BNParams(Structure):
     _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p)]
 
 
+class SavedForward(Structure):
+    _fields_ = [("acts", POINTER(c_void_p)), ("pre", POINTER(c_void_p)), ("bn_record", c_void_p), ("zprime", c_void_p)]
+
+
 class ConvLayer(Structure):
     _fields_ = [("cin", c_int), ("cout", c_int), ("relu", c_int),
                 ("weight_host", POINTER(c_float)), ("scale_host", POINTER(c_float)),
@@ -69,8 +73,13 @@ SIGNATURES = {
     "deqsci_adjoint_solve": (c_int, [_P, _P, _P, _P, POINTER(SolverOpts), _P, c_size_t, POINTER(SolverResult),
                                      c_int, c_int, c_int, c_int, _P]),
     "deqsci_denoiser_activation_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
-    "deqsci_iterate_save": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int,
-                                    c_int, _P]),
+    "deqsci_iterate_save": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(SavedForward), c_int, c_int,
+                                    c_int, c_int, _P]),
+    "deqsci_iterate_train_save": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, c_size_t, POINTER(BNParams), c_float,
+                                          c_float, POINTER(SavedForward), c_int, c_int, c_int, c_int, _P]),
+    "deqsci_backward_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "deqsci_backward_weights": (c_int, [_P, _P, POINTER(SavedForward), POINTER(_P), _P, c_float, c_float, POINTER(_P),
+                                        POINTER(_P), POINTER(_P), _P, c_size_t, c_int, c_int, c_int, c_int, _P]),
     "deqsci_denoise_residual_masked": (c_int, [_P, _P, _P, _P, c_size_t, POINTER(_P), c_int, c_int, c_int, c_int, _P]),
     "deqsci_adjoint_solve_denoiser": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, POINTER(SolverOpts), c_float, _P, c_size_t,
                                               POINTER(SolverResult), c_int, c_int, c_int, c_int, _P]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeqsci.so")
-SOURCES = ["api.cu", "driver.cu", "profile.cu", "tma_host.cu", "bn_train.cu", "optim.cu", "gap.cu", "anderson.cu", "conv_cc.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc_first.cu", "conv_tc_last.cu"]
+SOURCES = ["api.cu", "driver.cu", "profile.cu", "tma_host.cu", "bn_train.cu", "optim.cu", "backward.cu", "gap.cu", "anderson.cu", "conv_cc.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc_first.cu", "conv_tc_last.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

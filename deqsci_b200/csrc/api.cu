@@ -59,10 +59,22 @@ bool tc2_supported(int Hc, int Wc);
 int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long plane_elems, const uint8_t* wimg,
                             const float* scale, const float* bias, int relu, int NF, int Hc, int Wc,
                             cudaStream_t st, double* stats = nullptr, const __half* mask = nullptr);
+// backward.cu
+size_t backward_scratch_floats();
+int act_bwd_launch(const __half* g, const __half* act, const __half* pre, const float* rec, const float* gamma,
+                   __half* out, long long plane_elems, long long count, float* scratch, float* d_gamma, float* d_beta,
+                   cudaStream_t st);
+int wgrad_hidden_launch(const __half* a, const __half* d, long long plane_elems, int NF, int Hc, int Wc, float* scratch,
+                        float* d_weight, cudaStream_t st);
+int wgrad_last_launch(int cout, const __half* a, long long plane_elems, const float* gsc, int B, int H, int W, int T,
+                      float* scratch, float* d_weight, cudaStream_t st);
+int wgrad_first_launch(int cin, const __half* d, long long plane_elems, const float* zp, float sigma, int NF, int H, int W,
+                       float* scratch, float* d_weight, cudaStream_t st);
+int backward_begin(float* scratch, const float* g, float* gsc, float scale, long long n, cudaStream_t st);
 int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift,
                     const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                    long long count, int relu, cudaStream_t st);
+                    long long count, int relu, cudaStream_t st, const __half* src = nullptr, float* record = nullptr);
 size_t tc_weight_image_bytes(bool split, int cout);
 void tc_pack_weights(const float* w, int cout, bool split, uint8_t* img);
 void tc_pack_map(int cout, bool split, int32_t* map);
@@ -315,7 +327,8 @@ extern "C" size_t deqsci_denoiser_workspace_bytes(const deqsci_denoiser* h, int 
 static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, const float* y, const float* phi,
                      const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes, int B,
                      int H, int W, int T, void* stream, const deqsci_bn_params* bn = nullptr, float momentum = 0.f,
-                     float eps = 0.f, void* const* save = nullptr, const void* const* masks = nullptr) {
+                     float eps = 0.f, const deqsci_saved_forward* sv = nullptr, const void* const* masks = nullptr) {
+  void* const* save = sv ? sv->acts : nullptr;
   Geometry g;
   int rc = geometry(h, B, H, W, T, &g);
   if (rc) return rc;
@@ -366,6 +379,10 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
     rc = gap_prep_launch(h->kind, z, y, phi, phi_sum, zprime_ws, act[1], in_plane, sigma, B, H, W, T, fuse_gap,
                          zprime_planar, st);
     if (rc) return rc;
+    if (sv && sv->zprime) {          // the first layer's wgrad input: the frames z' (frame-planar)
+      DEQSCI_CHECK_ARG(zprime_planar, "saving z' needs the fused GAP step and the tensor-core first / last layers");
+      DEQSCI_CUDA(cudaMemcpyAsync(sv->zprime, zprime_ws, (size_t)B * H * W * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     rc = conv_first_tc_launch(act[1], in_plane, save ? reinterpret_cast<__half*>(save[0]) : act[0], g.plane_elems,
                               L0.w_tc, L0.scale, L0.bias, relu_of(0, L0.relu), g.NF, g.Hc, g.Wc, st, mask_of(0));
   } else {
@@ -383,12 +400,14 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
                                 g.Wc, st);
     else if (bn && bn[i].running_mean) {      // a BatchNorm follows this conv (gamma / beta are NULL for affine=False)
       // train mode: raw conv + per-channel statistics, then batch-statistics BatchNorm (+ ReLU) in place
-      rc = conv_hidden_2cta_launch(a_in, a_out, g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
+      // backward pass wanted: the raw conv output is kept in pre[i], the normalised activation goes to acts[i]
+      __half* c_out = (sv && sv->pre && sv->pre[i]) ? reinterpret_cast<__half*>(sv->pre[i]) : a_out;
+      rc = conv_hidden_2cta_launch(a_in, c_out, g.plane_elems, L.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc,
                                    g.Wc, st, bn_stats);
       if (rc == DEQSCI_OK)
         rc = bn_train_launch(a_out, g.plane_elems, bn_stats, num_sms(), bn_scale_shift, bn[i].gamma, bn[i].beta,
                              bn[i].running_mean, bn[i].running_var, momentum, eps, (long long)g.NF * g.Hc * g.Wc,
-                             L.relu, st);
+                             L.relu, st, c_out, (sv && sv->bn_record) ? sv->bn_record + (size_t)i * 4 * kHidden : nullptr);
     } else if (h->precision == DEQSCI_PREC_TC_SPLIT && tc2_supported(g.Hc, g.Wc))
       rc = conv_hidden_2cta_launch(a_in, a_out, g.plane_elems, L.w_tc2, L.scale, L.bias, relu_of(i, L.relu), g.NF,
                                    g.Hc, g.Wc, st, nullptr, mask_of(i));
@@ -432,11 +451,107 @@ extern "C" size_t deqsci_denoiser_activation_bytes(const deqsci_denoiser* h, int
 
 extern "C" int deqsci_iterate_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
                                    const float* phi_sum, float sigma, float* out, void* workspace,
-                                   size_t workspace_bytes, void* const* acts_host, int B, int H, int W, int T,
+                                   size_t workspace_bytes, const deqsci_saved_forward* save, int B, int H, int W, int T,
                                    void* stream) {
-  DEQSCI_CHECK_ARG(acts_host != nullptr, "iterate_save: null activation table");
+  DEQSCI_CHECK_ARG(save != nullptr && save->acts != nullptr, "iterate_save: null activation table");
   return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream, nullptr,
-                   0.f, 0.f, acts_host, nullptr);
+                   0.f, 0.f, save, nullptr);
+}
+
+extern "C" int deqsci_iterate_train_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                                         const float* phi_sum, float sigma, float* out, void* workspace,
+                                         size_t workspace_bytes, const deqsci_bn_params* bn_host, float momentum,
+                                         float eps, const deqsci_saved_forward* save, int B, int H, int W, int T,
+                                         void* stream) {
+  DEQSCI_CHECK_ARG(bn_host != nullptr, "iterate_train_save: null BatchNorm table");
+  DEQSCI_CHECK_ARG(save != nullptr && save->acts != nullptr, "iterate_train_save: null activation table");
+  return run_stack(h, true, z, y, phi, phi_sum, sigma, out, workspace, workspace_bytes, B, H, W, T, stream, bn_host,
+                   momentum, eps, save, nullptr);
+}
+
+// ---- weight gradients of one iterate-map call (kernels in backward.cu) --------------------------------------
+extern "C" size_t deqsci_backward_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T) {
+  Geometry g;
+  if (geometry(h, B, H, W, T, &g) != DEQSCI_OK) return 0;
+  // the adjoint plan's own stack workspace (K-packed plane of the last layer's dgrad), three gradient plane pairs,
+  // the scaled upstream cube and the reduction scratch
+  return 2048 + deqsci_denoiser_workspace_bytes(h, B, H, W, T) + 3 * g.act_bytes + g.zprime_bytes +
+         align_up(backward_scratch_floats() * sizeof(float), 1024);
+}
+
+extern "C" int deqsci_backward_weights(const deqsci_denoiser* h, const deqsci_denoiser* adj,
+                                       const deqsci_saved_forward* sv, const float* const* gamma, const float* grad,
+                                       float grad_scale, float sigma, float* const* d_weight, float* const* d_gamma,
+                                       float* const* d_beta, void* workspace, size_t workspace_bytes, int B, int H, int W,
+                                       int T, void* stream) {
+  DEQSCI_CHECK_ARG(h && adj && sv && sv->acts && sv->zprime && grad && d_weight && workspace, "backward_weights: null pointer");
+  Geometry g;
+  int rc = geometry(h, B, H, W, T, &g);
+  if (rc) return rc;
+  const int nl = (int)h->layers.size();
+  DEQSCI_CHECK_ARG((int)adj->layers.size() == nl && adj->kind == h->kind, "backward_weights: adjoint plan does not match");
+  DEQSCI_CHECK_ARG(h->precision == DEQSCI_PREC_TC_SPLIT && adj->precision == DEQSCI_PREC_TC_SPLIT && tcf_supported(g.Wc) &&
+                       tc2_supported(g.Hc, g.Wc),
+                   "backward_weights needs precision tc_split and conv images wider than 64 pixels (got %dx%d)", g.Hc, g.Wc);
+  DEQSCI_CHECK_ARG(grad_scale > 0.f && grad_scale < 3.0e38f, "backward_weights: grad_scale must be positive and finite");
+  const size_t need = deqsci_backward_workspace_bytes(h, B, H, W, T);
+  if (workspace_bytes < need) {
+    set_error("backward_weights: workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+    return DEQSCI_ERR_WORKSPACE;
+  }
+  for (int i = 0; i < nl; ++i) DEQSCI_CHECK_ARG(d_weight[i] != nullptr, "backward_weights: d_weight[%d] is null", i);
+  for (int i = 0; i < nl - 1; ++i) DEQSCI_CHECK_ARG(sv->acts[i] != nullptr, "backward_weights: acts[%d] is null", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const size_t den_bytes = deqsci_denoiser_workspace_bytes(h, B, H, W, T);
+  uint8_t* den_ws = ws;
+  __half* G[2] = {reinterpret_cast<__half*>(ws + align_up(den_bytes, 1024)),
+                  reinterpret_cast<__half*>(ws + align_up(den_bytes, 1024) + g.act_bytes)};
+  __half* D = reinterpret_cast<__half*>(ws + align_up(den_bytes, 1024) + 2 * g.act_bytes);
+  float* gsc = reinterpret_cast<float*>(ws + align_up(den_bytes, 1024) + 3 * g.act_bytes);
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(gsc) + g.zprime_bytes);
+  const long long count = (long long)g.NF * g.Hc * g.Wc;
+  const long long ncube = (long long)B * H * W * T;
+  auto act_of = [&](int i) { return reinterpret_cast<const __half*>(sv->acts[i]); };
+  auto pre_of = [&](int i) { return (sv->pre && sv->pre[i]) ? reinterpret_cast<const __half*>(sv->pre[i]) : nullptr; };
+
+  // upstream: the network's output enters f as  z' - noise  ->  gn = -grad (scaled)
+  if ((rc = backward_begin(scratch, grad, gsc, grad_scale, ncube, st))) return rc;
+  const Layer& LL = h->layers[nl - 1];
+  if ((rc = wgrad_last_launch(LL.cout, act_of(nl - 2), g.plane_elems, gsc, B, H, W, T, scratch, d_weight[nl - 1], st))) return rc;
+  // dgrad of the last layer: the adjoint plan's FIRST layer (gap_prep builds its K-packed input from the cube; for
+  // FFDNet the sigma channel's adjoint weights are zero)
+  {
+    uint8_t* dws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(den_ws), 1024));
+    float* zp_dummy = reinterpret_cast<float*>(dws);
+    __half* kplane = reinterpret_cast<__half*>(dws + g.zprime_bytes + g.act_bytes);      // the stack's act[1]
+    const long long in_plane = (long long)g.NF * g.Hc * g.Wc * kPrepChannels;
+    if ((rc = gap_prep_launch(h->kind, gsc, nullptr, nullptr, nullptr, zp_dummy, kplane, in_plane, 0.f, B, H, W, T, false,
+                              false, st))) return rc;
+    const Layer& A0 = adj->layers[0];
+    if ((rc = conv_first_tc_launch(kplane, in_plane, G[0], g.plane_elems, A0.w_tc, nullptr, nullptr, 0, g.NF, g.Hc, g.Wc,
+                                   st))) return rc;
+  }
+  int cur = 0;
+  for (int i = nl - 2; i >= 0; --i) {
+    const __half* pre = pre_of(i);
+    const float* rec = pre ? sv->bn_record + (size_t)i * 4 * kHidden : nullptr;
+    if (pre) DEQSCI_CHECK_ARG(sv->bn_record != nullptr, "backward_weights: BatchNorm layer %d without a record", i);
+    if ((rc = act_bwd_launch(G[cur], act_of(i), pre, rec, (pre && gamma) ? gamma[i] : nullptr, D, g.plane_elems, count,
+                             scratch, (pre && d_gamma) ? d_gamma[i] : nullptr, (pre && d_beta) ? d_beta[i] : nullptr, st)))
+      return rc;
+    if (i == 0) {
+      const Layer& L0 = h->layers[0];
+      return wgrad_first_launch(L0.cin, D, g.plane_elems, sv->zprime, sigma, g.NF, H, W, scratch, d_weight[0], st);
+    }
+    if ((rc = wgrad_hidden_launch(act_of(i - 1), D, g.plane_elems, g.NF, g.Hc, g.Wc, scratch, d_weight[i], st))) return rc;
+    // da_{i-1} = conv(dc_i, W_i^T flipped): adjoint layer nl-1-i
+    const Layer& A = adj->layers[nl - 1 - i];
+    if ((rc = conv_hidden_2cta_launch(D, G[cur ^ 1], g.plane_elems, A.w_tc2, nullptr, nullptr, 0, g.NF, g.Hc, g.Wc, st)))
+      return rc;
+    cur ^= 1;
+  }
+  return DEQSCI_OK;
 }
 
 extern "C" int deqsci_denoise_residual_masked(const deqsci_denoiser* h_adjoint, const float* vin, float* out,

@@ -12,7 +12,7 @@ namespace deqsci {
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_partials, float* __restrict__ scale_shift,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                                   float eps, double count) {
+                                   float eps, double count, float* __restrict__ record) {
   pdl_launch_dependents();       // launched with programmatic stream serialization: see launch_pdl (common.cuh)
   pdl_wait_predecessor();
   // 1024 threads: 8 row groups x 128 columns of the per-CTA partials; every column is added up in a fixed
@@ -40,6 +40,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_parti
   const float sc = g * rsqrtf((float)var + eps);
   scale_shift[c] = sc;
   scale_shift[kHidden + c] = b - (float)mean * sc;
+  if (record) {                      // kept for the backward pass: scale, shift, batch mean, 1/sqrt(var + eps)
+    record[c] = sc;
+    record[kHidden + c] = b - (float)mean * sc;
+    record[2 * kHidden + c] = (float)mean;
+    record[3 * kHidden + c] = rsqrtf((float)var + eps);
+  }
   if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
   if (running_var) {
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -47,7 +53,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int n_parti
   }
 }
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act, long long plane_elems,
+// src == act: in place; otherwise the raw conv output planes `src` are kept (backward pass) and `act` receives the result
+__global__ void __launch_bounds__(256) bn_apply_kernel(__half* act, const __half* src, long long plane_elems,
                                                        const float* __restrict__ scale_shift, int relu) {
   __shared__ float ss[2 * kHidden];
   pdl_launch_dependents();
@@ -57,8 +64,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act,
   const long long n_vec = plane_elems / 8;     // 8 channels (16 bytes per plane) per step
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
        i += (long long)gridDim.x * blockDim.x) {
-    uint4 h4 = *reinterpret_cast<const uint4*>(act + i * 8);
-    uint4 l4 = *reinterpret_cast<const uint4*>(act + plane_elems + i * 8);
+    uint4 h4 = *reinterpret_cast<const uint4*>(src + i * 8);
+    uint4 l4 = *reinterpret_cast<const uint4*>(src + plane_elems + i * 8);
     __half* hh = reinterpret_cast<__half*>(&h4);
     __half* ll = reinterpret_cast<__half*>(&l4);
     const int c0 = (int)((i * 8) & (kHidden - 1));
@@ -80,14 +87,15 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__half* __restrict__ act,
 // run are zero); scale_shift: device float[128] scratch
 int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                    long long count, int relu, cudaStream_t st) {
+                    long long count, int relu, cudaStream_t st, const __half* src, float* record) {
+  if (!src) src = act;
   DEQSCI_CUDA(launch_pdl(bn_finalize_kernel, 1, 8 * 2 * kHidden, 0, st, stats, n_partials, scale_shift, gamma, beta,
-                         running_mean, running_var, momentum, eps, (double)count));
+                         running_mean, running_var, momentum, eps, (double)count, record));
   long long blocks = (plane_elems / 8 + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   ProfScope prof(PK_GAP, st);
-  DEQSCI_CUDA(launch_pdl(bn_apply_kernel, (unsigned)blocks, 256, 0, st, act, plane_elems, (const float*)scale_shift, relu));
+  DEQSCI_CUDA(launch_pdl(bn_apply_kernel, (unsigned)blocks, 256, 0, st, act, src, plane_elems, (const float*)scale_shift, relu));
   return DEQSCI_OK;
 }
 

@@ -47,6 +47,22 @@ def _destroy(handle):
         pass
 
 
+class SavedActivations:
+    """What a forward call kept for the backward passes (device buffers + the ctypes view the C-ABI takes)."""
+
+    def struct(self):
+        P = ctypes.c_void_p
+        n = len(self.acts)
+        self._acts_tab = (P * n)(*[a.data_ptr() for a in self.acts])
+        self._pre_tab = (P * n)(*[p.data_ptr() if p is not None else None for p in self.pre])
+        sf = _lib.SavedForward()
+        sf.acts = ctypes.cast(self._acts_tab, ctypes.POINTER(P))
+        sf.pre = ctypes.cast(self._pre_tab, ctypes.POINTER(P)) if any(p is not None for p in self.pre) else None
+        sf.bn_record = self.bn_record.data_ptr() if self.bn_record is not None else None
+        sf.zprime = self.zprime.data_ptr() if self.zprime is not None else None
+        return sf
+
+
 class NativeDenoiser:
     """kind: 'ffdnet' | 'dncnn'.  layers: list of dicts {weight [O,I,3,3], scale [O]|None,
     bias [O]|None, relu bool} (host arrays).  Lives on `device`."""
@@ -81,7 +97,9 @@ class NativeDenoiser:
         self._fin = weakref.finalize(self, _destroy, handle)
         self._ws = None
         self._rws = None
+        self._bws = None
         self.num_layers = len(layers)
+        self._layer_shapes = [(int(arr[i].cout), int(arr[i].cin)) for i in range(len(layers))]
 
     def update_weights(self, weights):
         """Refreshes the plan's conv weights from the live device tensors (deqsci_denoiser_update_weights):
@@ -148,9 +166,12 @@ class NativeDenoiser:
         return out
 
     # ---- backward of a conv / ReLU stack on the same kernels (tag 'denoiser', DE-GAP-CNN) ------------------
-    def iterate_save(self, z, y, phi, phi_sum, sigma=0.0):
-        """One call of the iterate map that also keeps every hidden activation (deqsci_iterate_save).  Returns
-        (out, acts): acts[i] = output planes of conv layer i, fp16 [2, B*T, Hc, Wc, 64] (hi plane, lo plane)."""
+    def iterate_save(self, z, y, phi, phi_sum, sigma=0.0, bn_modules=None, want_zprime=False):
+        """One call of the iterate map that also keeps what a backward pass needs (deqsci_iterate_save, or
+        deqsci_iterate_train_save when bn_modules is given: batch-statistics BatchNorm, running statistics updated).
+        Returns (out, saved): saved.acts[i] = output planes of conv layer i, fp16 [2, B*T, Hc, Wc, 64] (hi, lo);
+        saved.pre[i] = the raw conv output of a layer followed by BatchNorm (train mode); saved.bn_record
+        [num_layers, 256] = scale, shift, batch mean, 1/sqrt(var + eps); saved.zprime [B,T,H,W] = the input frames."""
         z, y = _req(z, "z", 4), _req(y, "y", 3)
         phi, phi_sum = _bcast_phi(_req(phi, "Phi", 4), z), _bcast_phi(_req(phi_sum, "Phi_sum", 3), z)
         self._check_dev(z)
@@ -158,13 +179,70 @@ class NativeDenoiser:
         out = torch.empty_like(z)
         ws = self._workspace(B, H, W, T)
         nbytes = lib().deqsci_denoiser_activation_bytes(self._h, B, H, W, T)
-        acts = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(self.num_layers - 1)]
-        ptrs = (ctypes.c_void_p * len(acts))(*[a.data_ptr() for a in acts])
+        n = self.num_layers - 1
+        saved = SavedActivations()
+        saved.shape = (B, H, W, T)
+        saved.sigma = float(sigma)
+        saved.acts = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(n)]
+        saved.pre = [None] * n
+        saved.bn_record = None
+        saved.zprime = torch.empty((B, T, H, W), dtype=torch.float32, device=self.device) if want_zprime else None
+        if bn_modules is not None:
+            saved.pre = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) if bn_modules[i] is not None else None
+                         for i in range(n)]
+            saved.bn_record = torch.zeros((self.num_layers, 256), dtype=torch.float32, device=self.device)
+        sf = saved.struct()
         with torch.cuda.device(self.device):
-            check(lib().deqsci_iterate_save(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
-                                            float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), ptrs, B, H, W, T,
-                                            _stream(z)), "deqsci_iterate_save")
-        return out, acts
+            if bn_modules is None:
+                check(lib().deqsci_iterate_save(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(), phi_sum.data_ptr(),
+                                                float(sigma), out.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(sf),
+                                                B, H, W, T, _stream(z)), "deqsci_iterate_save")
+            else:
+                arr, momentum, eps = self._bn_table(bn_modules)
+                check(lib().deqsci_iterate_train_save(self._h, z.data_ptr(), y.data_ptr(), phi.data_ptr(),
+                                                      phi_sum.data_ptr(), float(sigma), out.data_ptr(), ws.data_ptr(),
+                                                      ws.numel(), arr, momentum, eps, ctypes.byref(sf), B, H, W, T,
+                                                      _stream(z)), "deqsci_iterate_train_save")
+                for bn in bn_modules:
+                    if bn is not None and bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked += 1
+        return out, saved
+
+    def backward_weights(self, adjoint, saved, grad, gammas, grad_scale=None):
+        """Weight gradients of the call that produced `saved` (deqsci_backward_weights): returns
+        (d_weight [list per conv layer], d_gamma, d_beta [lists, None where no BatchNorm follows]).  `adjoint`: the
+        adjoint plan; gammas[i]: the BatchNorm weight tensor after conv layer i or None."""
+        grad = _req(grad, "grad", 4)
+        self._check_dev(grad)
+        B, H, W, T = saved.shape
+        if tuple(grad.shape) != (B, H, W, T):
+            raise DeqsciError("backward_weights: grad %s does not match the saved call %s" % (tuple(grad.shape), saved.shape))
+        if saved.zprime is None:
+            raise DeqsciError("backward_weights: the forward call did not keep z' (want_zprime=True)")
+        if grad_scale is None:
+            gmax = float(grad.abs().max())
+            grad_scale = 2.0 ** (-np.floor(np.log2(gmax))) if np.isfinite(gmax) and gmax > 0 else 1.0
+            grad_scale = float(min(max(grad_scale, 2.0 ** -60), 2.0 ** 60))
+        nl = self.num_layers
+        shapes = self._layer_shapes
+        dW = [torch.empty((co, ci, 3, 3), dtype=torch.float32, device=self.device) for (co, ci) in shapes]
+        has_bn = [i < nl - 1 and saved.pre[i] is not None for i in range(nl)]
+        dG = [torch.empty(64, dtype=torch.float32, device=self.device) if has_bn[i] else None for i in range(nl)]
+        dBt = [torch.empty(64, dtype=torch.float32, device=self.device) if has_bn[i] else None for i in range(nl)]
+        P = ctypes.c_void_p
+        tab = lambda ts: (P * nl)(*[t.data_ptr() if t is not None else None for t in ts])
+        gam = [gammas[i] if (has_bn[i] and gammas[i] is not None) else None for i in range(nl)]
+        need = lib().deqsci_backward_workspace_bytes(self._h, B, H, W, T)
+        if self._bws is None or self._bws.numel() < need:
+            self._bws = None
+            self._bws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        sf = saved.struct()
+        with torch.cuda.device(self.device):
+            check(lib().deqsci_backward_weights(self._h, adjoint._h, ctypes.byref(sf), tab(gam), grad.data_ptr(),
+                                                float(grad_scale), float(saved.sigma), tab(dW), tab(dG), tab(dBt),
+                                                self._bws.data_ptr(), self._bws.numel(), B, H, W, T, _stream(grad)),
+                  "deqsci_backward_weights")
+        return dW, dG, dBt
 
     def _mask_table(self, masks):
         if len(masks) != self.num_layers - 1:
@@ -342,6 +420,45 @@ class NativePlanCache:
         tensors = [p for p in self.parameters() if p.dim() == 4] if train else \
             list(self.parameters()) + list(self.buffers())
         return tuple((id(t), t._version, t.data_ptr()) for t in tensors)
+
+    # ---- the stack run backwards: layers reversed, weights transposed and flipped --------------------------
+    def _plan_kind(self):
+        raise NotImplementedError
+
+    def _adjoint_conv_weights(self):
+        """Conv weight tensors of the stack in forward order, or None when the stack is not a plain sequence of
+        3x3 bias-free convolutions the adjoint plan can be derived from."""
+        return None
+
+    def native_adjoint_plan(self, device):
+        """NativeDenoiser on W'[c][o][ky][kx] = W[o][c][2-ky][2-kx], layers in reverse order: its layers are the
+        dgrads of the forward stack (backward solve of tag 'denoiser', weight-gradient pass).  FFDNet: the adjoint
+        of the last layer takes the 4 pixel-unshuffled gradient channels behind a zero sigma channel, and the plan's
+        own last layer (64 -> 4, never run) is zeros.  Refreshed on the device when the weights have changed."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        ws = self._adjoint_conv_weights()
+        if ws is None:
+            raise DeqsciError("no adjoint plan for this stack")
+        kind = self._plan_kind()
+        sig = tuple((id(w), w._version, w.data_ptr()) for w in ws)
+        with torch.no_grad():
+            adj = [w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous() for w in reversed(ws)]
+            if kind == "ffdnet":
+                adj[0] = torch.cat([torch.zeros_like(adj[0][:, :1]), adj[0]], 1).contiguous()
+                adj[-1] = torch.zeros((4, 64, 3, 3), dtype=torch.float32, device=adj[0].device)
+        hit = self.__dict__.get("_native_adjoint")
+        if hit is not None and hit[1].device == device and hit[1].num_layers == len(adj):
+            if hit[0] != sig:
+                hit[1].update_weights(adj)
+                self.__dict__["_native_adjoint"] = (sig, hit[1])
+            return self.__dict__["_native_adjoint"][1]
+        layers = [{"weight": a.float().cpu(), "scale": None, "bias": None, "relu": i < len(adj) - 1}
+                  for i, a in enumerate(adj)]
+        plan = NativeDenoiser(kind, layers, getattr(self, "precision", None), device)
+        self.__dict__["_native_adjoint"] = (sig, plan)
+        return plan
 
     def native_plan(self, device, precision=None, train=False):
         precision = precision or getattr(self, "precision", None) or default_precision()

@@ -138,6 +138,12 @@ class FFDNet(nn.Module, NativePlanCache):
     def _plan_live_weights(self, train=False):
         return sequential_live_weights(self.intermediate_dncnn.itermediate_dncnn, train)
 
+    def _plan_kind(self):
+        return "ffdnet"
+
+    def _adjoint_conv_weights(self):
+        return [m.weight for m in self.intermediate_dncnn.itermediate_dncnn if isinstance(m, nn.Conv2d)]
+
     def native_train_ok(self, z):
         """Train-mode forward solve (no_grad) on the native kernels: cube [B,H,W,T] whose half-resolution
         frames are wider than 64 pixels (the CTA-pair conv kernel's tiles)."""

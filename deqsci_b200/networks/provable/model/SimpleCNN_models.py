@@ -79,28 +79,13 @@ class DnCNN(nn.Module, NativePlanCache):
                 and os.environ.get("DEQSCI_TC_PAIR", "1") != "0" and os.environ.get("DEQSCI_TC_FIRST", "1") != "0"
                 and int(z.shape[2]) > 64)
 
-    def native_adjoint_plan(self, device):
-        """NativeDenoiser built from the layers in reverse order with W'[c][o][ky][kx] = W[o][c][2-ky][2-kx]; refreshed
-        on the device (no host copy) when the weights have changed since it was packed."""
-        from ....native import NativeDenoiser
-        device = torch.device(device)
-        if device.type == "cuda" and device.index is None:
-            device = torch.device("cuda", torch.cuda.current_device())
-        ws = [m.weight for m in self.dncnn if isinstance(m, nn.Conv2d)]
-        sig = tuple((id(w), w._version, w.data_ptr()) for w in ws)
-        with torch.no_grad():
-            adj = [w.detach().permute(1, 0, 2, 3).flip(2, 3).contiguous() for w in reversed(ws)]
-        hit = self.__dict__.get("_native_adjoint")
-        if hit is not None and hit[1].device == device and hit[1].num_layers == len(adj):
-            if hit[0] != sig:
-                hit[1].update_weights(adj)
-                self.__dict__["_native_adjoint"] = (sig, hit[1])
-            return self.__dict__["_native_adjoint"][1]
-        layers = [{"weight": a.float().cpu(), "scale": None, "bias": None, "relu": i < len(adj) - 1}
-                  for i, a in enumerate(adj)]
-        plan = NativeDenoiser("dncnn", layers, getattr(self, "precision", None), device)
-        self.__dict__["_native_adjoint"] = (sig, plan)
-        return plan
+    def _plan_kind(self):
+        return "dncnn"
+
+    def _adjoint_conv_weights(self):
+        if not all(isinstance(m, (nn.Conv2d, nn.ReLU, nn.BatchNorm2d)) for m in self.dncnn):
+            return None
+        return [m.weight for m in self.dncnn if isinstance(m, nn.Conv2d)]
 
     def _stateless_in_train_mode(self):
         return all(isinstance(m, (nn.Conv2d, nn.ReLU)) for m in self.dncnn)

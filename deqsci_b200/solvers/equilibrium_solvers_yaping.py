@@ -145,6 +145,15 @@ class EquilibriumProxGradSCI(nn.Module):
             return plan.iterate_train(z, y, Phi, Phi_sum, sigma, op.bn_slots(), out=out)
         if not z.is_cuda and not (self.nonlinear_op.training and torch.is_grad_enabled()):
             raise DeqsciError("EquilibriumProxGradSCI inference on %s: deqsci_b200 has no CPU path" % z.device)
+        from ..backward import native_backward_ok, native_iterate
+        if torch.is_grad_enabled() and native_backward_ok(self, z, y, Phi, Phi_sum):
+            # the graph-attached call as ONE native autograd node: tensor-core forward that keeps the activations,
+            # weight gradients from csrc/backward.cu (no autograd tape through cuDNN)
+            sigma = 0.0
+            if tag == 'ffdnet':
+                self.n_sigma_frames = bsz * c
+                sigma = float(self._advance_sigma(y))
+            return native_iterate(self, z, y, Phi, Phi_sum, sigma)
         return self._autograd_forward(z, y, Phi, Phi_sum)
 
     def _autograd_forward(self, z, y, Phi, Phi_sum):

@@ -371,7 +371,8 @@ class DEQFixedPoint(nn.Module):
         if native_den:
             with torch.no_grad():
                 # the reference's second call f(z0): its values are not needed, its activations are
-                _, acts = op_.native_plan(z.device).iterate_save(z0.detach(), x, Phi, Phi_sum, 0.0)
+                _, saved_ = op_.native_plan(z.device).iterate_save(z0.detach(), x, Phi, Phi_sum, 0.0)
+                acts = saved_.acts
             f0 = None
         elif native_vjp:
             # the reference's second call f(z0) only feeds autograd.grad; its side effects (sigma step,

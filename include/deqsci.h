@@ -249,9 +249,9 @@ int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_s
 /* The implicit-differentiation hook for tag 'denoiser' (DE-GAP-CNN, solvers/new_equilibrium_utils_yaping.py:271-277):
  * the reference evaluates f0 = f(z0) with a graph and runs andersonexp on g -> autograd.grad(f0, z0, g) + grad, i.e.
  * one full backward pass of the conv stack per solver iteration.  Here:
- *  - deqsci_iterate_save is deqsci_iterate that also keeps every hidden activation: acts_host[i]
- *    (i = 0 .. num_layers-2, device buffers of deqsci_denoiser_activation_bytes() each) receives the output planes of
- *    conv layer i ([hi plane | lo plane], channels-last [B*T,Hc,Wc,64] fp16);
+ *  - deqsci_iterate_save is deqsci_iterate that also keeps every hidden activation (deqsci_saved_forward below):
+ *    save->acts[i] (i = 0 .. num_layers-2, device buffers of deqsci_denoiser_activation_bytes() each) receives the
+ *    output planes of conv layer i ([hi plane | lo plane], channels-last [B*T,Hc,Wc,64] fp16);
  *  - the VJP of the conv / ReLU stack is the SAME kernels run on an ADJOINT plan -- created with
  *    deqsci_denoiser_create from the layers in reverse order, weights transposed and flipped
  *    (W'[c][o][ky][kx] = W[o][c][2-ky][2-kx]) -- whose ReLUs are replaced by the sign of the saved activations:
@@ -262,10 +262,46 @@ int deqsci_adjoint_solve(const float* grad, const float* phi, const float* phi_s
  *    evaluated on vjp_scale * g and scaled back, so that loss gradients of ~1e-7 per element sit in fp16's normal
  *    range inside the conv kernels; the solver state keeps its own magnitudes (lam * I is scale-dependent).
  * Plain conv / ReLU stacks (no folded BatchNorm), precision TC_SPLIT, conv images wider than 64 pixels. */
+/* What a forward call keeps for the backward passes (all device buffers, owned by the caller; the tables themselves
+ * are host arrays with one entry per conv layer 0 .. num_layers-2):
+ *   acts[i]    output planes of conv layer i AFTER BatchNorm / ReLU (deqsci_denoiser_activation_bytes() each);
+ *   pre[i]     train mode only: the raw conv output planes of a layer followed by BatchNorm (NULL entries / NULL
+ *              table otherwise);
+ *   bn_record  train mode only: 256 floats per conv layer: scale, shift, batch mean, 1/sqrt(var+eps) (64 each);
+ *   zprime     [B,T,H,W] floats: the network's input frames z' (frame-planar), the first layer's wgrad input
+ *              (may be NULL when only the activations are wanted). */
+typedef struct {
+  void* const* acts;
+  void* const* pre;
+  float* bn_record;
+  float* zprime;
+} deqsci_saved_forward;
+
 size_t deqsci_denoiser_activation_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
 int deqsci_iterate_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
                         const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
-                        void* const* acts_host, int B, int H, int W, int T, void* stream);
+                        const deqsci_saved_forward* save, int B, int H, int W, int T, void* stream);
+/* deqsci_iterate_train (batch-statistics BatchNorm, running statistics updated) that keeps the same things. */
+int deqsci_iterate_train_save(const deqsci_denoiser* h, const float* z, const float* y, const float* phi,
+                              const float* phi_sum, float sigma, float* out, void* workspace, size_t workspace_bytes,
+                              const deqsci_bn_params* bn_host, float momentum, float eps,
+                              const deqsci_saved_forward* save, int B, int H, int W, int T, void* stream);
+
+/* Weight gradients of that call (csrc/backward.cu): the backward pass the reference runs through autograd / cuDNN for
+ * its ONE graph-attached f evaluation (solvers/new_equilibrium_utils_yaping.py:268; loss.backward()).  `grad` [B,H,W,T]
+ * is dL/d(out); the gradient w.r.t. the iterate itself is not produced (the reference's z* is detached).  Per conv
+ * layer i: d_weight[i] <- dL/dW_i ([cout,cin,3,3] fp32); for a layer followed by train-mode BatchNorm (save->pre[i]
+ * non-NULL) gamma[i] is its weight (NULL = 1) and d_gamma[i] / d_beta[i] receive its parameter gradients.
+ * dgrad = the tensor-core conv kernels on the ADJOINT plan `adjoint` (layers reversed, weights transposed and flipped;
+ * its LAST layer is never run and may hold zeros); wgrad, ReLU and BatchNorm backward = CUDA-core kernels with
+ * two-stage fixed-order reductions.  grad_scale: power of two applied to `grad` on entry and divided out of every
+ * result (the gradient planes are fp16 pairs; deeper layers are re-scaled on the device).  sigma as in the forward call.
+ * Needs precision TC_SPLIT and conv images wider than 64 pixels. */
+size_t deqsci_backward_workspace_bytes(const deqsci_denoiser* h, int B, int H, int W, int T);
+int deqsci_backward_weights(const deqsci_denoiser* h, const deqsci_denoiser* adjoint, const deqsci_saved_forward* save,
+                            const float* const* gamma, const float* grad, float grad_scale, float sigma,
+                            float* const* d_weight, float* const* d_gamma, float* const* d_beta,
+                            void* workspace, size_t workspace_bytes, int B, int H, int W, int T, void* stream);
 int deqsci_denoise_residual_masked(const deqsci_denoiser* h_adjoint, const float* vin, float* out,
                                    void* workspace, size_t workspace_bytes, const void* const* masks_host,
                                    int B, int H, int W, int T, void* stream);

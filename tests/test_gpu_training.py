@@ -252,7 +252,8 @@ def test_masked_adjoint_vjp_vs_autograd(train_wide_vectors):
     f0 = solver._autograd_forward(z0, y, Phi, Ps)
     want = torch.autograd.grad(f0, z0, vec)[0]
     with torch.no_grad():
-        out, acts = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)
+        out, saved = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)
+        acts = saved.acts
         assert rel_l2(out.cpu().numpy(), f0.detach().cpu().numpy()) <= 2e-5          # same forward values
         adj = op.native_adjoint_plan(dev)
         got = ops.gap_vjp(adj.denoise_residual_masked(vec, list(reversed(acts))), Phi, Ps)
@@ -292,9 +293,53 @@ def test_masked_adjoint_vjp_vs_autograd(train_wide_vectors):
     with torch.no_grad():
         for p_ in op.parameters():
             p_.mul_(1.02)
-        _, acts1 = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)
+        acts1 = op.native_plan(dev).iterate_save(z0.detach(), y, Phi, Ps, 0.0)[1].acts
         adj1 = op.native_adjoint_plan(dev)
         assert adj1 is adj
         got1 = ops.gap_vjp(adj1.denoise_residual_masked(vec, list(reversed(acts1))), Phi, Ps)
         assert rel_l2(got1.cpu().numpy(), torch_vjp(acts1).cpu().numpy()) <= 2e-5
     assert rel_l2(got1.cpu().numpy(), got.cpu().numpy()) > 1e-3
+
+
+@pytest.mark.parametrize("d", ["SimpleCNN", "ffdnet"])
+def test_native_weight_gradients_vs_autograd(train_wide_vectors, d, monkeypatch):
+    """The graph-attached iterate-map call as ONE native autograd node (deqsci_b200/backward.py: tensor-core forward that
+    keeps the activations, csrc/backward.cu for ReLU / train-mode BatchNorm backward and wgrad, the adjoint plan's
+    tensor-core dgrads) against the same call through PyTorch autograd / cuDNN: values, every parameter gradient,
+    BatchNorm running statistics -- with an upstream gradient of realistic size (~1e-7 per element)."""
+    import copy
+    from test_gpu_parity import build_solver
+    from deqsci_b200.backward import native_backward_ok
+    from deqsci_b200.utils.cg_utils import Phi_sum_
+    dev = torch.device("cuda", 0)
+    v = train_wide_vectors
+    a = build_solver(d, dev)
+    a.train()
+    a.nonlinear_op.train()
+    b = copy.deepcopy(a)
+    gt, Phi, y = (torch.from_numpy(v[k]).to(dev) for k in ("gt", "Phi", "y"))
+    Ps = Phi_sum_(Phi)
+    g = torch.Generator().manual_seed(5)
+    z = gt + 0.05 * torch.randn(gt.shape, generator=g).to(dev)
+    assert native_backward_ok(a, z, y, Phi, Ps)
+    fa = a(z, y, Phi, Ps)                                   # native node
+    assert type(fa.grad_fn).__name__.startswith("NativeIterate")
+    up = (2.0 * (fa.detach() - gt) / gt.numel()).contiguous()      # the MSE loss's gradient: ~1e-7 per element
+    (fa * up).sum().backward()
+    monkeypatch.setenv("DEQSCI_NATIVE_BACKWARD", "0")
+    fb = b(z, y, Phi, Ps)                                   # autograd / cuDNN
+    assert not type(fb.grad_fn).__name__.startswith("NativeIterate")
+    (fb * up).sum().backward()
+    assert rel_l2(fa.detach().cpu().numpy(), fb.detach().cpu().numpy()) <= 2e-5
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    errs = {}
+    for k in pb:
+        assert pa[k].grad is not None and pb[k].grad is not None, k
+        errs[k] = rel_l2(pa[k].grad.cpu().numpy(), pb[k].grad.cpu().numpy())
+    print("parameter-gradient rel-L2 vs autograd:", {k.split("nonlinear_op.")[-1]: float("%.2e" % e) for k, e in errs.items()})
+    assert max(errs.values()) <= 1e-3, errs
+    for (ka, ba), (kb, bb) in zip(a.named_buffers(), b.named_buffers()):
+        if ka.endswith("running_mean") or ka.endswith("running_var"):
+            assert rel_l2(ba.cpu().numpy(), bb.cpu().numpy()) <= 1e-4, ka
+        if ka.endswith("num_batches_tracked"):
+            assert int(ba) == int(bb)
