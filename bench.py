@@ -299,7 +299,7 @@ def ncu_traffic(kernel, batch):
         b, "" if b == batch else ", scaled to batch %d" % batch)
 
 
-def train_step_bench(dev, rank, world, steps=5, warmup=2, batch=2, max_iter=100, denoiser="ffdnet", data=None):
+def train_step_bench(dev, rank, world, steps=5, warmup=3, batch=2, max_iter=100, denoiser="ffdnet", data=None):
     """Config 5: implicit-differentiation training steps (reference training/sci_equilibrium_training.py:54-75) on
     `batch` synthetic measurements per GPU: forward solve + graph-attached call + backward solve + gradient
     all-reduce over the ranks + Adam.  Step and all-reduce(+optimizer) times are CUDA-event times, max over ranks."""
@@ -465,7 +465,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras and args.denoiser == "ffdnet":
         # config 5 under the same launch: the NCCL gradient all-reduce is exercised at every N >= 2
-        extras["train_step"] = train_step_bench(dev, rank, world, steps=args.train_steps, warmup=2, batch=args.train_batch,
+        extras["train_step"] = train_step_bench(dev, rank, world, steps=args.train_steps, warmup=3, batch=args.train_batch,
                                                 data=args.data)
     if not args.no_extras and world == 1 and args.denoiser == "ffdnet":
         side = {}
@@ -478,7 +478,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "recon_per_s": B * 3 / (ms_side / 1e3), "and_maxiters": 100, "batch": B}
             del dq
         # config 5 with the DnCNN-style denoiser: its backward solve runs on the masked-adjoint conv stack
-        ts = train_step_bench(dev, rank, world, steps=3, warmup=1, batch=args.train_batch, denoiser="SimpleCNN", data=args.data)
+        ts = train_step_bench(dev, rank, world, steps=3, warmup=3, batch=args.train_batch, denoiser="SimpleCNN", data=args.data)
         side["DE-GAP-CNN train_step"] = {"ms_per_step": ts["ms_per_step"], "batch": args.train_batch, "and_maxiters": 100,
                                          "backward_res": ts["backward_res"]}
         extras["side"] = side

@@ -101,7 +101,8 @@ class NativeIterate(torch.autograd.Function):
                 gammas[i] = p_.detach()
         adj = op.native_adjoint_plan(grad.device)
         dW, dG, dB = ctx.plan.backward_weights(adj, ctx.saved, grad.contiguous(), gammas)
-        ctx.saved = None                                   # the activations are dead after one backward pass
+        ctx.saved.release()                                # the activations are dead after one backward pass
+        ctx.saved = None
         grads = []
         for p_, role, i in layout:
             g = {'w': dW, 'g': dG, 'b': dB}[role][i]

@@ -25,6 +25,7 @@ constexpr int kRedCtas = 296;                  // partial rows of the per-channe
 constexpr int kWgTile = 32;                    // wgrad tile: kWgRows x 32 pixels
 constexpr int kWgRows = 4;
 constexpr int kWgMaxCtas = 148;
+constexpr int kThinCtas = 592;                 // thin-layer wgrads: latency-bound streaming loops, 4 CTAs per SM
 
 // scal[0] = cumulative scale of the gradient planes currently in flight, scal[1] = this layer's factor
 struct ActBwdParams {
@@ -69,22 +70,35 @@ __global__ void __launch_bounds__(256) act_bwd_reduce_kernel(const ActBwdParams 
   }
 }
 
-// one block of 64 threads: totals in fp64 (fixed order), BatchNorm parameter gradients, the layer's scale factor
+// one block of 1024 threads (16 row groups x 64 channels): totals in fp64 in a fixed order, BatchNorm parameter
+// gradients, the layer's scale factor
 // coef[0..63] = per-channel multiplier, coef[64..127] = m1, coef[128..191] = m2 (means of dy and dy*xhat)
-__global__ void act_bwd_finalize_kernel(const float* __restrict__ partial, int n_partials, const float* __restrict__ rec,
-                                        const float* __restrict__ gamma, double count, float* __restrict__ coef,
-                                        float* __restrict__ scal, float* __restrict__ d_gamma,
-                                        float* __restrict__ d_beta) {
+__global__ void __launch_bounds__(1024) act_bwd_finalize_kernel(const float* __restrict__ partial, int n_partials,
+                                                                 const float* __restrict__ rec,
+                                                                 const float* __restrict__ gamma, double count,
+                                                                 float* __restrict__ coef, float* __restrict__ scal,
+                                                                 float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+  __shared__ double s_sum[16][kHidden], s_sx[16][kHidden];
+  __shared__ float s_mx[16][kHidden];
   __shared__ float s_bound[kHidden];
-  const int c = threadIdx.x;
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  {
+    double a = 0.0, b = 0.0;
+    float m = 0.f;
+    for (int k = grp; k < n_partials; k += 16) {
+      const float* o = partial + (size_t)k * 3 * kHidden;
+      a += (double)o[c];
+      b += (double)o[kHidden + c];
+      m = fmaxf(m, o[2 * kHidden + c]);
+    }
+    s_sum[grp][c] = a; s_sx[grp][c] = b; s_mx[grp][c] = m;
+  }
+  __syncthreads();
+  if (grp != 0) return;
   double sum = 0.0, sx = 0.0;
   float mx = 0.f;
-  for (int k = 0; k < n_partials; ++k) {
-    const float* o = partial + (size_t)k * 3 * kHidden;
-    sum += (double)o[c];
-    sx += (double)o[kHidden + c];
-    mx = fmaxf(mx, o[2 * kHidden + c]);
-  }
+#pragma unroll
+  for (int g = 0; g < 16; ++g) { sum += s_sum[g][c]; sx += s_sx[g][c]; mx = fmaxf(mx, s_mx[g][c]); }
   const float cum = scal[0];
   float mult = 1.f, m1 = 0.f, m2 = 0.f, bound = mx;
   if (rec) {
@@ -98,7 +112,8 @@ __global__ void act_bwd_finalize_kernel(const float* __restrict__ partial, int n
   }
   coef[c] = mult; coef[kHidden + c] = m1; coef[2 * kHidden + c] = m2;
   s_bound[c] = bound;
-  __syncthreads();
+  // only warps 0 and 1 (threads 0..63) are left: a named barrier over those 64 threads
+  asm volatile("bar.sync 1, 64;" ::: "memory");
   if (c == 0) {
     float b = 0.f;
     for (int k = 0; k < kHidden; ++k) b = fmaxf(b, s_bound[k]);
@@ -295,28 +310,28 @@ __global__ void __launch_bounds__(256) wgrad_last_kernel(const __half* __restric
   for (int o = 0; o < CO; ++o)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[o][t] = 0.f;
+  // every INPUT pixel q once (its 64 channels: one coalesced load per plane); the output pixels it feeds are
+  // p = q - tap + 1, whose gradients are a handful of scalars shared by the 64 threads (broadcast loads)
   const long long n_px = (long long)B * T * Hc * Wc;
   for (long long px = (long long)blockIdx.x * 4 + sub; px < n_px; px += (long long)gridDim.x * 4) {
     const int x = (int)(px % Wc);
     const int y = (int)((px / Wc) % Hc);
     const int nf = (int)(px / ((long long)Wc * Hc));
     const int b = nf / T, t = nf % T;
-    float gv[CO];
-#pragma unroll
-    for (int o = 0; o < CO; ++o) {
-      const int r = SC == 2 ? (o >> 1) : 0, s = SC == 2 ? (o & 1) : 0;
-      gv[o] = gsc[(((long long)b * H + (SC * y + r)) * W + (SC * x + s)) * T + t];
-    }
+    const long long i = px * kHidden + c;
+    const float av = join_f16(a[i], a[plane_elems + i]);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xx = x + kx - 1;
+        const int yy = y - ky + 1, xx = x - kx + 1;          // output pixel that sees q through tap (ky, kx)
         if (yy < 0 || yy >= Hc || xx < 0 || xx >= Wc) continue;
-        const long long i = (((long long)nf * Hc + yy) * Wc + xx) * kHidden + c;
-        const float av = join_f16(a[i], a[plane_elems + i]);
 #pragma unroll
-        for (int o = 0; o < CO; ++o) acc[o][ky * 3 + kx] = fmaf(gv[o], av, acc[o][ky * 3 + kx]);
+        for (int o = 0; o < CO; ++o) {
+          const int r = SC == 2 ? (o >> 1) : 0, s = SC == 2 ? (o & 1) : 0;
+          const float gv = __ldg(gsc + (((long long)b * H + (SC * yy + r)) * W + (SC * xx + s)) * T + t);
+          acc[o][ky * 3 + kx] = fmaf(gv, av, acc[o][ky * 3 + kx]);
+        }
       }
   }
   __shared__ float s_red[4][CO * 9][kHidden + 1];
@@ -395,7 +410,7 @@ __global__ void set_scal_kernel(float* scal, float cum) { scal[0] = cum; scal[1]
 // ---- launchers (used by api.cu) -----------------------------------------------------------------------------
 size_t backward_scratch_floats() {
   // per-channel reduction partials, coefficients, scalars, wgrad partials (hidden layer: the largest)
-  return (size_t)kRedCtas * 3 * kHidden + 3 * kHidden + 64 + (size_t)kWgMaxCtas * kHidden * kHidden * 9;
+  return (size_t)kRedCtas * 3 * kHidden + 3 * kHidden + 64 + std::max((size_t)kWgMaxCtas * kHidden * kHidden * 9, (size_t)kThinCtas * kHidden * 5 * 9);
 }
 
 int act_bwd_launch(const __half* g, const __half* act, const __half* pre, const float* rec, const float* gamma,
@@ -408,7 +423,7 @@ int act_bwd_launch(const __half* g, const __half* act, const __half* pre, const 
   const long long n_px = plane_elems / kHidden;
   const int blocks = (int)std::min<long long>(kRedCtas, (n_px + 3) / 4);
   act_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(p, partial);
-  act_bwd_finalize_kernel<<<1, kHidden, 0, st>>>(partial, blocks, rec, gamma, (double)count, coef, scal, d_gamma, d_beta);
+  act_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, blocks, rec, gamma, (double)count, coef, scal, d_gamma, d_beta);
   const long long n_vec = plane_elems / 8;
   const int ablocks = (int)std::min<long long>((n_vec + 255) / 256, (long long)num_sms() * 16);
   act_bwd_apply_kernel<<<ablocks, 256, 0, st>>>(p, coef, scal);
@@ -439,7 +454,7 @@ int wgrad_last_launch(int cout, const __half* a, long long plane_elems, const fl
                       float* scratch, float* d_weight, cudaStream_t st) {
   float* scal = scratch + (size_t)kRedCtas * 3 * kHidden + 3 * kHidden;
   float* partial = scal + 64;
-  const int ctas = std::min(kWgMaxCtas, num_sms());
+  const int ctas = kThinCtas;
   if (cout == 4) wgrad_last_kernel<4><<<ctas, 256, 0, st>>>(a, plane_elems, gsc, B, H, W, T, partial);
   else if (cout == 1) wgrad_last_kernel<1><<<ctas, 256, 0, st>>>(a, plane_elems, gsc, B, H, W, T, partial);
   else { set_error("backward: last layer with %d outputs unsupported", cout); return DEQSCI_ERR_INVALID; }
@@ -453,7 +468,7 @@ int wgrad_first_launch(int cin, const __half* d, long long plane_elems, const fl
                        float* scratch, float* d_weight, cudaStream_t st) {
   float* scal = scratch + (size_t)kRedCtas * 3 * kHidden + 3 * kHidden;
   float* partial = scal + 64;
-  const int ctas = std::min(kWgMaxCtas, num_sms());
+  const int ctas = kThinCtas;
   if (cin == 5) wgrad_first_kernel<5><<<ctas, 256, 0, st>>>(d, plane_elems, zp, sigma, NF, H, W, partial);
   else if (cin == 1) wgrad_first_kernel<1><<<ctas, 256, 0, st>>>(d, plane_elems, zp, sigma, NF, H, W, partial);
   else { set_error("backward: first layer with %d inputs unsupported", cin); return DEQSCI_ERR_INVALID; }

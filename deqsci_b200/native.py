@@ -48,7 +48,16 @@ def _destroy(handle):
 
 
 class SavedActivations:
-    """What a forward call kept for the backward passes (device buffers + the ctypes view the C-ABI takes)."""
+    """What a forward call kept for the backward passes (device buffers + the ctypes view the C-ABI takes).
+    release() hands the big plane buffers back to the plan's pool, so a training loop re-uses the same ~2 GB every
+    step instead of going through the allocator (whose growth phase costs tens of milliseconds per step)."""
+    _pool = None
+
+    def release(self):
+        if self._pool is not None:
+            for t in list(self.acts) + [p for p in self.pre if p is not None]:
+                self._pool.append(t)
+        self.acts, self.pre, self._pool = [], [], None
 
     def struct(self):
         P = ctypes.c_void_p
@@ -183,13 +192,20 @@ class NativeDenoiser:
         saved = SavedActivations()
         saved.shape = (B, H, W, T)
         saved.sigma = float(sigma)
-        saved.acts = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(n)]
+        pool = self.__dict__.setdefault("_plane_pool", [])
+
+        def take():
+            for k, t in enumerate(pool):
+                if t.numel() == nbytes:
+                    return pool.pop(k)
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        saved._pool = pool
+        saved.acts = [take() for _ in range(n)]
         saved.pre = [None] * n
         saved.bn_record = None
         saved.zprime = torch.empty((B, T, H, W), dtype=torch.float32, device=self.device) if want_zprime else None
         if bn_modules is not None:
-            saved.pre = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) if bn_modules[i] is not None else None
-                         for i in range(n)]
+            saved.pre = [take() if bn_modules[i] is not None else None for i in range(n)]
             saved.bn_record = torch.zeros((self.num_layers, 256), dtype=torch.float32, device=self.device)
         sf = saved.struct()
         with torch.cuda.device(self.device):

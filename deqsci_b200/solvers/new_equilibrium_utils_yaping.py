@@ -389,6 +389,7 @@ class DEQFixedPoint(nn.Module):
                 # adjoint layer i is gated by the activation of forward layer L-2-i (hi plane = start of the buffer)
                 g, self.backward_res = op_.native_adjoint_plan(z.device).adjoint_solve(
                     grad.contiguous(), Phi, Phi_sum, masks=list(reversed(acts)), **self.kwargs)
+                saved_.release()                       # (the stream orders the buffers' next use behind the solve)
                 return g
             if (native_vjp and self.solver is andersonexp and os.environ.get("DEQSCI_DRIVER", "1") != "0"
                     and set(self.kwargs) <= {"m", "lam", "max_iter", "tol", "beta"}
