@@ -346,7 +346,10 @@ def train_step_bench(dev, rank, world, steps=5, warmup=3, batch=2, max_iter=100,
                               "(no waiting): the exchange + update itself",
             "allreduce_floats": int(sync.numel),
             "allreduce": sync.describe(), "measurements_per_s": world * batch * 1e3 / float(np.mean(step_ms)),
-            "forward_res": deq.forward_res, "backward_res": deq.backward_res, "loss_first_last": [losses[0], losses[-1]]}
+            "forward_res": deq.forward_res, "backward_res": deq.backward_res, "loss_first_last": [losses[0], losses[-1]],
+            "backward": ("native: one autograd node -- tensor-core forward keeping the activations, csrc/backward.cu wgrad / ReLU / "
+                         "BatchNorm backward, tensor-core dgrads on the adjoint plan (no cuDNN kernel in the step)"
+                         if os.environ.get("DEQSCI_NATIVE_BACKWARD", "1") != "0" else "PyTorch autograd / cuDNN fp32")}
 
 
 def eager_gpu_bar(dev, solver, y, phi, tf32, max_iter=MAX_ITER):
