@@ -92,6 +92,9 @@ class NativeIterate(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
+        if ctx.saved is None:
+            raise RuntimeError("NativeIterate: the saved activations were released by the first backward pass "
+                               "(retain_graph / double backward is not supported; DEQSCI_NATIVE_BACKWARD=0 uses autograd)")
         op, seq = ctx.op, stack_of(ctx.op)
         layout = parameter_layout(seq)
         n_conv = ctx.plan.num_layers
