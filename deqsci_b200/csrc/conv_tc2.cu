@@ -35,16 +35,27 @@ namespace tc2 {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 320;
-constexpr int kSlots = 4;                         // rolling ring of input rows
+constexpr int kSlotsMax = 4;                      // rolling ring of input rows (3 in the wide row-stationary mode)
 constexpr int kPlaneBytes = 17 * 1024;            // 130 pixels x 128 B, rounded up to the 1 KB swizzle atom
 constexpr int kSlotBytes = 2 * kPlaneBytes;       // hi + lo
 constexpr int kTxBytes = 2 * (kTileM + 2) * 128;  // bytes one CTA's TMA delivers per row
-constexpr int kTapBytesB = 64 * 128;              // this CTA's half of the B tile of one tap
-constexpr int kWBytes = 9 * kTapBytesB;           // 72 KB per CTA
 constexpr int kStageBytes = 2048;                 // per epilogue warp: 32 pixels x 32 channels fp16
-constexpr int kAccCols = 192;                     // main/corr1 interleaved (128) + corr2 (64)
+constexpr int kAccCols = 192;                     // output-stationary: main/corr1 interleaved (128) + corr2 (64), 2 buffers
+constexpr int kAccColsRS = 128;                   // row-stationary: main (64) + both corrections (64), 4 buffers
+constexpr int kAccBufsMax = 4;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = 1024 + kWBytes + kSlots * kSlotBytes + 8 * kStageBytes + 1024;
+// Issue modes (template parameter MODE of the kernel, DEQSCI_TC_RS):
+//   0  output-stationary: per output row 9 taps x {N = 128 on Ah, N = 64 on Al'}
+//   1  row-stationary, nine N = 64 instructions per (kx, k) slice, A-collector hints
+//   2  row-stationary wide: three N = 128 (Ah x [Wh | Wl']) + three N = 64 (Al' x Wh) per slice, hints; needs the
+//      96-row weight tiles (one 32-row block duplicated) and gives up one ring slot for them
+__host__ __device__ constexpr int tap_rows(int mode) { return mode == 2 ? 96 : 64; }        // this CTA's B rows per tap
+__host__ __device__ constexpr int tap_bytes(int mode) { return tap_rows(mode) * 128; }
+__host__ __device__ constexpr int w_bytes(int mode) { return 9 * tap_bytes(mode); }         // 72 / 108 KB per CTA
+__host__ __device__ constexpr int n_slots(int mode) { return mode == 2 ? 3 : 4; }
+__host__ __device__ constexpr int smem_bytes(int mode) {
+  return w_bytes(mode) + n_slots(mode) * kSlotBytes + 8 * kStageBytes + 1024;               // mode 2: exactly 227 KB
+}
 
 using namespace ptx;   // single-CTA mbarrier / TMA / tcgen05 wrappers (tc_ptx.cuh); below: the cluster / cta_group::2 forms
 
@@ -96,6 +107,22 @@ __device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with an A-operand collector hint: the tensor core keeps the A tile it fetched from shared memory
+// (MODE 1 = fill, SASS .A_KEEP) and later instructions take it from there instead of reading shared memory again
+// (2 = use, .A_REUSE.A_KEEP; 3 = lastuse, .A_REUSE).  ACC false overwrites D (first product of an accumulator).
+template <int MODE, bool ACC>
+__device__ __forceinline__ void umma2_f16_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+#define DEQSCI_UMMA2(Q)                                                                                   \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                        \
+               "tcgen05.mma.cta_group::2.kind::f16" Q " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),        \
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(ACC ? 1u : 0u)                                   \
+               : "memory")
+  if (MODE == 1) DEQSCI_UMMA2(".collector::a::fill");
+  else if (MODE == 2) DEQSCI_UMMA2(".collector::a::use");
+  else if (MODE == 3) DEQSCI_UMMA2(".collector::a::lastuse");
+  else DEQSCI_UMMA2("");
+#undef DEQSCI_UMMA2
+}
 // arrive (once all prior MMAs of this thread retired) on the barrier at the same offset in both CTAs
 __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
   asm volatile(
@@ -138,20 +165,93 @@ __device__ __forceinline__ Strip decode(const Params& p, long long strip) {
   return s;
 }
 
+
+// Collector hint of the idx-th of `total` consecutive instructions that share one A tile.
+__host__ __device__ constexpr int collector_mode(int idx, int total) {
+  return total == 1 ? 0 : idx == 0 ? 1 : idx == total - 1 ? 3 : 2;
+}
+
+// Row-stationary issue of ONE input row (both CTAs' rows, M = 256).  Each (kx, k) slice of the row's hi plane is
+// multiplied with Wh and Wl' of every output row the input row feeds (ky = 0, 1, 2 -> output rows q, q-1, q-2; L0..L2
+// say which of them exist), the slice of the lo plane with their Wh -- consecutive instructions on the same A tile, so
+// the tensor core fetches an activation tile from shared memory once instead of three times (collector hints).
+// d0..d2: accumulators of those output rows, 128 columns: main and both correction products (same 2^-11 scale,
+// one accumulator).  WIDE = false: nine N = 64 instructions per slice, columns [0,64) main, [64,128) corrections.
+// WIDE = true: three N = 128 (Ah x 64 rows of each CTA, tile rows [32,96)) + three N = 64 (Al' x tile rows [0,32)),
+// columns [0,32) main 0-31 | [32,96) corrections 0-63 | [96,128) main 32-63.
+template <bool L0, bool L1, bool L2, bool WIDE>
+__device__ __forceinline__ void issue_row_rs(uint32_t a_row, uint32_t w_base, uint32_t d0, uint32_t d1, uint32_t d2) {
+  constexpr uint32_t idesc64 = make_idesc(256, 64), idesc128 = make_idesc(256, 128);
+  constexpr int n_live = (L0 ? 1 : 0) + (L1 ? 1 : 0) + (L2 ? 1 : 0);
+  constexpr int p1 = L0 ? 1 : 0, p2 = p1 + (L1 ? 1 : 0);       // position of ky = 1, 2 among the live rows
+  constexpr uint64_t kRows32 = (32 * 128) >> 4;                // descriptor step of 32 tile rows
+  constexpr int kTapB = tap_bytes(WIDE ? 2 : 1);
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) {
+    const uint64_t a_hi = make_sdesc(a_row + kx * 128);
+    const uint64_t a_lo = make_sdesc(a_row + kPlaneBytes + kx * 128);
+    const uint64_t b0 = make_sdesc(w_base + (0 * 3 + kx) * kTapB);
+    const uint64_t b1 = make_sdesc(w_base + (1 * 3 + kx) * kTapB);
+    const uint64_t b2 = make_sdesc(w_base + (2 * 3 + kx) * kTapB);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t ah = a_hi + 2 * k, al = a_lo + 2 * k;
+      if (WIDE) {
+        if (L0) {                     // ky = 0 opens the accumulator of output row q: its first product overwrites
+          if (kx == 0 && k == 0) umma2_f16_c<collector_mode(0, n_live), false>(d0, ah, b0 + kRows32 + 2 * k, idesc128);
+          else umma2_f16_c<collector_mode(0, n_live), true>(d0, ah, b0 + kRows32 + 2 * k, idesc128);
+        }
+        if (L1) umma2_f16_c<collector_mode(p1, n_live), true>(d1, ah, b1 + kRows32 + 2 * k, idesc128);
+        if (L2) umma2_f16_c<collector_mode(p2, n_live), true>(d2, ah, b2 + kRows32 + 2 * k, idesc128);
+        if (L0) umma2_f16_c<collector_mode(0, n_live), true>(d0 + 32, al, b0 + 2 * k, idesc64);
+        if (L1) umma2_f16_c<collector_mode(p1, n_live), true>(d1 + 32, al, b1 + 2 * k, idesc64);
+        if (L2) umma2_f16_c<collector_mode(p2, n_live), true>(d2 + 32, al, b2 + 2 * k, idesc64);
+      } else {
+        if (L0) {
+          if (kx == 0 && k == 0) {
+            umma2_f16_c<collector_mode(0, 2 * n_live), false>(d0, ah, b0 + 2 * k, idesc64);
+            umma2_f16_c<collector_mode(1, 2 * n_live), false>(d0 + 64, ah, b0 + kRows32 + 2 * k, idesc64);
+          } else {
+            umma2_f16_c<collector_mode(0, 2 * n_live), true>(d0, ah, b0 + 2 * k, idesc64);
+            umma2_f16_c<collector_mode(1, 2 * n_live), true>(d0 + 64, ah, b0 + kRows32 + 2 * k, idesc64);
+          }
+        }
+        if (L1) {
+          umma2_f16_c<collector_mode(2 * p1, 2 * n_live), true>(d1, ah, b1 + 2 * k, idesc64);
+          umma2_f16_c<collector_mode(2 * p1 + 1, 2 * n_live), true>(d1 + 64, ah, b1 + kRows32 + 2 * k, idesc64);
+        }
+        if (L2) {
+          umma2_f16_c<collector_mode(2 * p2, 2 * n_live), true>(d2, ah, b2 + 2 * k, idesc64);
+          umma2_f16_c<collector_mode(2 * p2 + 1, 2 * n_live), true>(d2 + 64, ah, b2 + kRows32 + 2 * k, idesc64);
+        }
+        if (L0) umma2_f16_c<collector_mode(0, n_live), true>(d0 + 64, al, b0 + 2 * k, idesc64);
+        if (L1) umma2_f16_c<collector_mode(p1, n_live), true>(d1 + 64, al, b1 + 2 * k, idesc64);
+        if (L2) umma2_f16_c<collector_mode(p2, n_live), true>(d2 + 64, al, b2 + 2 * k, idesc64);
+      }
+    }
+  }
+}
+
 // STATS = true (train-mode BatchNorm): additionally accumulates per-output-channel sum and sum of
 // squares of the values it writes (over valid pixels); every CTA writes its partial to p.stats[cta][128].
-template <bool STATS>
+// MODE: issue order, see the constants above (0 output-stationary, 2 accumulator buffers of 192 columns; 1 / 2
+// row-stationary, 4 buffers of 128 columns).
+template <bool STATS, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_constant__ CUtensorMap in_lo,
                         const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo,
                         const Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];          // swizzle atoms need the 1 KB alignment; no slack to
+  if ((smem_u32(smem) & 1023u) != 0) __trap();               // realign by hand in mode 2 (227 KB exactly)
+  constexpr int kSlots = n_slots(MODE), kWBytes = w_bytes(MODE), kTapBytesB = tap_bytes(MODE);
   uint8_t* w_s = smem;
   uint8_t* a_s = w_s + kWBytes;
   uint8_t* st_s = a_s + kSlots * kSlotBytes;                 // 8 x 2 KB store staging
   uint8_t* tail = st_s + 8 * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);        // [0] w, full[4], empty[4], tfull[2], tempty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);        // [0] w, full[4], empty[4], tfull[4], tempty[4]
+  constexpr bool RS = MODE != 0;
+  constexpr int kBufs = RS ? 4 : 2;
+  constexpr int kCols = RS ? kAccColsRS : kAccCols;
   float* aff_s = reinterpret_cast<float*>(tail + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
 
@@ -163,14 +263,14 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_w = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
-  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlots + s]); };
-  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlots + b]); };
-  auto bar_tempty = [&](int b) { return smem_u32(&bars[3 + 2 * kSlots + b]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlotsMax + s]); };
+  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlotsMax + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[1 + 2 * kSlotsMax + kAccBufsMax + b]); };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 16); }
+    for (int b = 0; b < kBufs; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 16); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -217,7 +317,43 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread, for the pair) =====================
-    if (leader && elect_one_sync()) {
+    if (RS && leader && elect_one_sync()) {
+      // row-stationary: walk the strip's R + 2 input rows; input row q feeds output rows q, q-1, q-2 (ky = 0, 1, 2)
+      const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
+      const int R = p.strip_rows;
+      int slot = 0;
+      uint32_t sphase = 0;
+      uint32_t g0 = 0;               // running output-row count: row g lives in accumulator buffer g % 4
+      for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+        for (int q = 0; q < R + 2; ++q) {
+          if (q < R) {               // a new output row opens: its buffer must have been drained
+            const uint32_t g = g0 + q;
+            mbar_wait(bar_tempty(g & 3), ((g >> 2) & 1) ^ 1);
+          }
+          mbar_wait(bar_full(slot), sphase);
+          tc_fence_after();
+          const uint32_t a_row = a_base + slot * kSlotBytes;
+          const uint32_t d0 = tmem_base + ((g0 + q) & 3) * kAccColsRS;
+          const uint32_t d1 = tmem_base + ((g0 + q - 1) & 3) * kAccColsRS;
+          const uint32_t d2 = tmem_base + ((g0 + q - 2) & 3) * kAccColsRS;
+          const int live = (q < R ? 1 : 0) | (q >= 1 && q - 1 < R ? 2 : 0) | (q >= 2 ? 4 : 0);
+          constexpr bool H = MODE == 2;      // wide instructions
+          switch (live) {
+            case 1: issue_row_rs<true, false, false, H>(a_row, w_base, d0, d1, d2); break;
+            case 2: issue_row_rs<false, true, false, H>(a_row, w_base, d0, d1, d2); break;
+            case 3: issue_row_rs<true, true, false, H>(a_row, w_base, d0, d1, d2); break;
+            case 4: issue_row_rs<false, false, true, H>(a_row, w_base, d0, d1, d2); break;
+            case 6: issue_row_rs<false, true, true, H>(a_row, w_base, d0, d1, d2); break;
+            default: issue_row_rs<true, true, true, H>(a_row, w_base, d0, d1, d2); break;
+          }
+          umma2_commit_mc(bar_empty(slot));                       // the input row is consumed (both CTAs)
+          if (q >= 2) umma2_commit_mc(bar_tfull((g0 + q - 2) & 3));   // output row q-2 is complete
+          if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+        }
+        g0 += R;
+      }
+    }
+    if (!RS && leader && elect_one_sync()) {
       constexpr uint32_t idesc_main = make_idesc(256, 128);
       constexpr uint32_t idesc_lo = make_idesc(256, 64);
       const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
@@ -262,7 +398,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
             umma2_commit_mc(bar_empty((dead + 2) % kSlots));
           }
           umma2_commit_mc(bar_tfull(buf));
-          if (++buf == 2) { buf = 0; tphase ^= 1; }
+          if (++buf == kBufs) { buf = 0; tphase ^= 1; }
         }
         first = wait_slot;
         first_phase = wait_phase;
@@ -274,7 +410,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int half = e >> 2;                      // output channels [32*half, +32)
     const uint32_t stage = smem_u32(st_s + e * kStageBytes);
-    const uint32_t tempty_leader0 = mapa(bar_tempty(0), 0), tempty_leader1 = mapa(bar_tempty(1), 0);
+    const uint32_t tempty_leader0 = mapa(bar_tempty(0), 0);      // the leader's tempty[b] = this + 8 b
     int buf = 0;
     uint32_t tphase = 0;
     float st_sum[STATS ? 32 : 1], st_sq[STATS ? 32 : 1];     // this thread's 32 channels, over all its pixels
@@ -305,14 +441,22 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
         }
         mbar_wait(bar_tfull(buf), tphase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccCols;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kCols;
         uint32_t hi_pk[16], lo_pk[16];
 #pragma unroll
         for (int part = 0; part < 2; ++part) {      // 16 channels at a time
           uint32_t acc[16], c1[16], c2[16];
-          tmem_ld16(t_row + half * 64 + part * 16, acc);
-          tmem_ld16(t_row + half * 64 + 32 + part * 16, c1);
-          tmem_ld16(t_row + 128 + half * 32 + part * 16, c2);
+          if (MODE == 2) {
+            tmem_ld16(t_row + half * 96 + part * 16, acc);
+            tmem_ld16(t_row + 32 + half * 32 + part * 16, c1);
+          } else if (MODE == 1) {
+            tmem_ld16(t_row + half * 32 + part * 16, acc);
+            tmem_ld16(t_row + 64 + half * 32 + part * 16, c1);
+          } else {
+            tmem_ld16(t_row + half * 64 + part * 16, acc);
+            tmem_ld16(t_row + half * 64 + 32 + part * 16, c1);
+            tmem_ld16(t_row + 128 + half * 32 + part * 16, c2);
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -321,8 +465,8 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
             const float sb[4] = {sb4.x, sb4.y, sb4.z, sb4.w};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              float a = fmaf(__uint_as_float(c1[i + u]) + __uint_as_float(c2[i + u]), kLoInvScale,
-                             __uint_as_float(acc[i + u]));
+              float a = fmaf(RS ? __uint_as_float(c1[i + u]) : __uint_as_float(c1[i + u]) + __uint_as_float(c2[i + u]),
+                             kLoInvScale, __uint_as_float(acc[i + u]));
               a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
               if (p.relu == 2) {         // gate by the saved activation's sign (fp16 hi half != +0)
                 const uint32_t mbits = (mkw[part * 8 + (i >> 1)] >> (16 * u)) & 0x7fffu;
@@ -342,11 +486,11 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
         // accumulator drained: hand the TMEM buffer back to the leader's MMA thread
         tc_fence_before();
         __syncwarp();
-        if (elect_one_sync()) mbar_arrive_cluster(buf == 0 ? tempty_leader0 : tempty_leader1);
+        if (elect_one_sync()) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
         // stage (64-byte swizzle: chunk ^= (row >> 1) & 3) and store the two planes with TMA
         const uint32_t row_addr = stage + lane * 64;
         const int sw = (lane >> 1) & 3;
-        if (p.debug_skip_store == 1) { if (++buf == 2) { buf = 0; tphase ^= 1; } continue; }
+        if (p.debug_skip_store == 1) { if (++buf == kBufs) { buf = 0; tphase ^= 1; } continue; }
         if (p.debug_skip_store == 2) {             // experiment: direct global stores, no smem staging
           const int wpx = s.w0 + quarter * 32 + lane;
           if (s.real && wpx < p.Wc && h < p.Hc) {
@@ -359,7 +503,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
               dl[q] = make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
             }
           }
-          if (++buf == 2) { buf = 0; tphase ^= 1; }
+          if (++buf == kBufs) { buf = 0; tphase ^= 1; }
           continue;
         }
 #pragma unroll
@@ -383,7 +527,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
             }
           }
         }
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
+        if (++buf == kBufs) { buf = 0; tphase ^= 1; }
       }
     }
     bulk_wait0();
@@ -426,21 +570,32 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 }  // namespace tc2
 
 // ---- host side -------------------------------------------------------------------------------
-size_t tc2_weight_image_bytes() { return 2 * (size_t)tc2::kWBytes; }
+// issue mode of the pair kernel, fixed for the process (it also decides the weight image layout)
+static int tc2_issue_mode() {
+  static const int mode = [] { const int m = env_int("DEQSCI_TC_RS", 2); return m < 0 || m > 2 ? 2 : m; }();
+  return mode;
+}
+size_t tc2_weight_image_bytes() { return 2 * (size_t)tc2::w_bytes(tc2_issue_mode()); }
 
-// w [64 cout][64 cin][3][3] fp32 -> [rank][tap][64 rows][128 B], rows of rank r: [0,32) = hi(W[32r + n]),
-// [32,64) = lo'(W[32r + n - 32]); K-major fp16 rows with the 128-byte swizzle.
+// w [64 cout][64 cin][3][3] fp32 -> [rank][tap][rows][128 B], K-major fp16 rows with the 128-byte swizzle.
+// Modes 0, 1 (64 rows): rows of rank r: [0,32) = hi(W[32r + n]), [32,64) = lo'(W[32r + n - 32]).
+// Mode 2 (96 rows): rank 0: [0,32) = [32,64) = hi(W[n % 32]), [64,96) = lo'(W[n - 64]);
+//                   rank 1: [0,32) = [64,96) = hi(W[32 + n % 32]), [32,64) = lo'(W[n]).
+//   The N = 128 instruction reads rows [32,96) of both CTAs, the N = 64 one rows [0,32): its 64 columns land on the
+//   64 lo' columns in the middle of the wide instruction's 128.
 template <class Emit>
 static void tc2_layout(Emit emit) {
+  const int mode = tc2_issue_mode(), rows = tc2::tap_rows(mode), tapb = tc2::tap_bytes(mode);
   for (int rank = 0; rank < 2; ++rank)
     for (int tap = 0; tap < 9; ++tap) {
       const int ky = tap / 3, kx = tap % 3;
-      for (int n = 0; n < 64; ++n) {
+      for (int n = 0; n < rows; ++n) {
         const int co = 32 * rank + (n & 31);
+        const bool lo = mode == 2 ? (rank == 0 ? n >= 64 : (n >= 32 && n < 64)) : n >= 32;
         for (int k = 0; k < 64; ++k) {
-          const size_t byte = ((size_t)rank * 9 + tap) * tc2::kTapBytesB + (size_t)n * 128 +
+          const size_t byte = ((size_t)rank * 9 + tap) * tapb + (size_t)n * 128 +
                               (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
-          emit(byte, ((co * 64 + k) * 3 + ky) * 3 + kx, n >= 32);
+          emit(byte, ((co * 64 + k) * 3 + ky) * 3 + kx, lo);
         }
       }
     }
@@ -493,17 +648,22 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   if ((rc = make_plane_map(&out_hi, act_out, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   if ((rc = make_plane_map(&out_lo, act_out + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
   const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
+  const int issue_mode = tc2_issue_mode();
   ProfScope prof(PK_CONV_HIDDEN, st);
+  auto launch = [&](auto kernel) {
+    const int smem = tc2::smem_bytes(issue_mode);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(kernel, (unsigned)(2 * pairs), tc2::kThreads, smem, st, in_hi, in_lo, out_hi, out_lo, p);
+  };
   if (stats) {
-    DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     tc2::kSmemBytes));
-    DEQSCI_CUDA(launch_pdl(tc2::conv_hidden_2cta_kernel<true>, (unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st,
-                           in_hi, in_lo, out_hi, out_lo, p));
+    if (issue_mode == 0) DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<true, 0>));
+    else if (issue_mode == 1) DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<true, 1>));
+    else DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<true, 2>));
   } else {
-    DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     tc2::kSmemBytes));
-    DEQSCI_CUDA(launch_pdl(tc2::conv_hidden_2cta_kernel<false>, (unsigned)(2 * pairs), tc2::kThreads, tc2::kSmemBytes, st,
-                           in_hi, in_lo, out_hi, out_lo, p));
+    if (issue_mode == 0) DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<false, 0>));
+    else if (issue_mode == 1) DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<false, 1>));
+    else DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<false, 2>));
   }
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
