@@ -43,6 +43,7 @@ AND_UPDATES = MAX_ITER - 2
 SEED = 20260117
 # algorithmic work: hidden 64->64 3x3 layers at 128x128 on 8 frames per measurement
 HIDDEN_FLOP_PER_LAUNCH_PER_MEAS = 2 * 9 * 64 * 64 * (H // 2) * (W // 2) * T
+N_HIDDEN = {"ffdnet": 13, "SimpleCNN": 3, "RealSN_SimpleCNN": 3}      # 64 -> 64 layers of each denoiser
 STACK_FLOP_PER_F_PER_MEAS = 2 * 9 * (5 * 64 + 13 * 64 * 64 + 64 * 4) * (H // 2) * (W // 2) * T
 
 
@@ -498,7 +499,9 @@ def run_gpu_arm(args, rank, world, local_rank):
     peaks, peak_src = measured_peaks()
     hid_ms = ms_sum[2] / max(n_samp[2], 1)
     res_div = 2 if args.denoiser == "ffdnet" else 1              # FFDNet convs run at half resolution
-    flop_per_launch = 2 * 9 * 64 * 64 * (H // res_div) * (W // res_div) * T * B
+    # hidden layers one launch covers: 1 (a kernel per layer) or the whole run (chained kernel, conv_tc2.cu)
+    layers_per_launch = max(1, int(round(N_HIDDEN[args.denoiser] * n_launch[1] / n_launch[2]))) if n_launch[2] else 1
+    flop_per_launch = 2 * 9 * 64 * 64 * (H // res_div) * (W // res_div) * T * B * layers_per_launch
     achieved = flop_per_launch / (hid_ms * 1e-3) / 1e12 if hid_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
@@ -507,8 +510,16 @@ def run_gpu_arm(args, rank, world, local_rank):
     shares = {kinds[i]: {"launches": int(n_launch[i]), "sampled": int(n_samp[i]), "avg_ms": avg[kinds[i]],
                          "est_ms_per_step": (avg[kinds[i]] * n_launch[i] / args.steps) if n_samp[i] else None}
               for i in range(k)}
-    hidden_kernel = ("conv_hidden_2cta_kernel" if args.precision == "tc_split" else "conv_mid_tc_kernel")
+    hidden_kernel = (("conv_hidden_chain_kernel" if layers_per_launch > 1 else "conv_hidden_2cta_kernel")
+                     if args.precision == "tc_split" else "conv_mid_tc_kernel")
     traffic, traffic_src = ncu_traffic("hidden", B) if (args.precision == "tc_split" and args.denoiser == "ffdnet") else (None, "n/a")
+    if traffic is not None:
+        # the committed capture is of one layer's launch (per-layer kernel) or of a whole run (chained kernel)
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")))["hidden"]
+        cap_layers = int(d.get("layers_per_launch", 13 if "chain" in d.get("kernel", "") else 1))
+        if cap_layers != layers_per_launch:
+            traffic = traffic * layers_per_launch / cap_layers
+            traffic_src += ", %d layer(s) per captured launch scaled to %d" % (cap_layers, layers_per_launch)
     # HBM-bound kernels (SURVEY 8(d) algorithmic bytes per measurement): GAP step 6,815,744 B per f call;
     # Anderson update (n = m = 5, beta = 1) 25,165,824 B per iteration over its three launches
     roof_hbm = {}
@@ -557,6 +568,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "traffic": traffic, "traffic_unit": "dram bytes per launch", "traffic_source": traffic_src,
                      "peak_source": peak_src + ", bf16 dense sustained",
                      "avg_launch_ms": hid_ms, "algorithmic_flop_per_launch": flop_per_launch,
+                     "hidden_layers_per_launch": layers_per_launch,
                      "issued_mma_flop_factor": 3 if args.precision == "tc_split" else 1,
                      "frac_issued": (3 if args.precision == "tc_split" else 1) * achieved / peak if peak else None,
                      "sampled_launches": int(n_samp[2])},

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,11 @@ int wgrad_last_launch(int cout, const __half* a, long long plane_elems, const fl
 int wgrad_first_launch(int cin, const __half* d, long long plane_elems, const float* zp, float sigma, int NF, int H, int W,
                        float* scratch, float* d_weight, cudaStream_t st);
 int backward_begin(float* scratch, const float* g, float* gsc, float scale, long long n, cudaStream_t st);
+bool tc2_chain_supported(int NF, int Hc, int Wc, int n_layers);
+size_t tc2_chain_flag_count(int NF, int Hc);
+int conv_hidden_chain_launch(__half* buf0, __half* buf1, long long plane_elems, int n_layers, const uint8_t* const* wimg,
+                             const float* const* scale, const float* const* bias, const int* relu, int NF, int Hc, int Wc,
+                             uint32_t* flags, uint32_t* epoch, cudaStream_t st);
 int bn_train_launch(__half* act, long long plane_elems, const double* stats, int n_partials, float* scale_shift,
                     const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
@@ -94,10 +100,19 @@ struct Layer {
 
 }  // namespace deqsci
 
+// per-stream state of the chained hidden-layer kernel (conv_tc2.cu): strip-ready flags + the launch epoch they count from
+struct ChainState {
+  uint32_t* flags = nullptr;
+  size_t count = 0;
+  uint32_t epoch = 0;
+};
+
 struct deqsci_denoiser {
   int kind = 0, precision = 0;
   std::vector<deqsci::Layer> layers;
   std::map<std::string, int32_t*> maps;   // device gather maps, built on the first update_weights call
+  mutable std::map<cudaStream_t, ChainState> chain;     // launches on one stream are ordered: they may share flags
+  mutable std::mutex chain_mutex;
 };
 
 using namespace deqsci;
@@ -123,6 +138,7 @@ extern "C" int deqsci_denoiser_destroy(deqsci_denoiser* h) {
     if (L.bias) cudaFree(L.bias);
   }
   for (auto& kv : h->maps) cudaFree(kv.second);
+  for (auto& kv : h->chain) if (kv.second.flags) cudaFree(kv.second.flags);
   delete h;
   return DEQSCI_OK;
 }
@@ -391,7 +407,37 @@ static int run_stack(const deqsci_denoiser* h, bool fuse_gap, const float* z, co
   }
   if (rc) return rc;
   int cur = 0;
-  for (int i = 1; i < nl - 1; ++i) {
+  // all hidden layers in ONE launch (CTA pairs stay resident, per-strip ready flags instead of kernel boundaries) when
+  // nothing between them needs a kernel boundary: no train-mode statistics, no saved activations, no masks
+  const bool chained = !bn && !save && !masks && h->precision == DEQSCI_PREC_TC_SPLIT && nl - 2 >= 2 &&
+                       tc2_chain_supported(g.NF, g.Hc, g.Wc, nl - 2);
+  if (chained) {
+    const uint8_t* wimg[32];
+    const float *sc[32], *bi[32];
+    int relu[32];
+    for (int i = 1; i < nl - 1; ++i) {
+      const Layer& L = h->layers[i];
+      wimg[i - 1] = L.w_tc2; sc[i - 1] = L.scale; bi[i - 1] = L.bias; relu[i - 1] = L.relu;
+    }
+    ChainState* cs;
+    {
+      std::lock_guard<std::mutex> lock(h->chain_mutex);
+      cs = &h->chain[st];
+      const size_t want = tc2_chain_flag_count(g.NF, g.Hc);
+      if (cs->count < want) {
+        if (cs->flags) { DEQSCI_CUDA(cudaStreamSynchronize(st)); DEQSCI_CUDA(cudaFree(cs->flags)); cs->flags = nullptr; cs->count = 0; }
+        DEQSCI_CUDA(cudaMalloc((void**)&cs->flags, want * sizeof(uint32_t)));
+        DEQSCI_CUDA(cudaMemsetAsync(cs->flags, 0, want * sizeof(uint32_t), st));
+        cs->count = want;
+        cs->epoch = 0;
+      }
+    }
+    rc = conv_hidden_chain_launch(act[0], act[1], g.plane_elems, nl - 2, wimg, sc, bi, relu, g.NF, g.Hc, g.Wc, cs->flags,
+                                  &cs->epoch, st);
+    if (rc) return rc;
+    cur = (nl - 2) & 1;
+  }
+  for (int i = 1; i < nl - 1 && !chained; ++i) {
     const Layer& L = h->layers[i];
     const __half* a_in = in_buf(i, cur);
     __half* a_out = out_buf(i, cur);

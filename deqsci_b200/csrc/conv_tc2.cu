@@ -146,13 +146,15 @@ struct Params {
   int debug_skip_store;       // experiment switch (DEQSCI_TC_DEBUG_SKIP_STORE): 1 = compute but do not store, 2 = direct st.global
   __half* dbg_out_hi;
   __half* dbg_out_lo;
+  int lookahead;              // issuer tests the next row's barriers ahead of time (DEQSCI_TC_LOOKAHEAD, default 1)
   const __half* mask;         // relu == 2: output (pixel, channel) is kept where this hi plane [NF,Hc,Wc,64] is > 0, else
                               // zeroed: the ReLU derivative of a saved forward activation (adjoint / VJP stacks)
 };
 
 struct Strip { int nf, h0, w0; bool real; };
 
-__device__ __forceinline__ Strip decode(const Params& p, long long strip) {
+template <class P>
+__device__ __forceinline__ Strip decode(const P& p, long long strip) {
   Strip s;
   s.real = strip < p.n_strips;
   if (!s.real) strip = p.n_strips - 1;
@@ -179,7 +181,8 @@ __host__ __device__ constexpr int collector_mode(int idx, int total) {
 // one accumulator).  WIDE = false: nine N = 64 instructions per slice, columns [0,64) main, [64,128) corrections.
 // WIDE = true: three N = 128 (Ah x 64 rows of each CTA, tile rows [32,96)) + three N = 64 (Al' x tile rows [0,32)),
 // columns [0,32) main 0-31 | [32,96) corrections 0-63 | [96,128) main 32-63.
-template <bool L0, bool L1, bool L2, bool WIDE>
+// KXB, KXE: the kx taps [KXB, KXE) of the row (the issuer splits a row in two to look ahead in between).
+template <bool L0, bool L1, bool L2, bool WIDE, int KXB, int KXE>
 __device__ __forceinline__ void issue_row_rs(uint32_t a_row, uint32_t w_base, uint32_t d0, uint32_t d1, uint32_t d2) {
   constexpr uint32_t idesc64 = make_idesc(256, 64), idesc128 = make_idesc(256, 128);
   constexpr int n_live = (L0 ? 1 : 0) + (L1 ? 1 : 0) + (L2 ? 1 : 0);
@@ -187,7 +190,7 @@ __device__ __forceinline__ void issue_row_rs(uint32_t a_row, uint32_t w_base, ui
   constexpr uint64_t kRows32 = (32 * 128) >> 4;                // descriptor step of 32 tile rows
   constexpr int kTapB = tap_bytes(WIDE ? 2 : 1);
 #pragma unroll
-  for (int kx = 0; kx < 3; ++kx) {
+  for (int kx = KXB; kx < KXE; ++kx) {
     const uint64_t a_hi = make_sdesc(a_row + kx * 128);
     const uint64_t a_lo = make_sdesc(a_row + kPlaneBytes + kx * 128);
     const uint64_t b0 = make_sdesc(w_base + (0 * 3 + kx) * kTapB);
@@ -232,6 +235,31 @@ __device__ __forceinline__ void issue_row_rs(uint32_t a_row, uint32_t w_base, ui
   }
 }
 
+// live: bit ky set = output row q - ky exists
+template <bool WIDE, int KXB, int KXE>
+__device__ __forceinline__ void issue_row_live(int live, uint32_t a_row, uint32_t w_base, uint32_t d0, uint32_t d1,
+                                               uint32_t d2) {
+  switch (live) {
+    case 1: issue_row_rs<true, false, false, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+    case 2: issue_row_rs<false, true, false, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+    case 3: issue_row_rs<true, true, false, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+    case 4: issue_row_rs<false, false, true, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+    case 6: issue_row_rs<false, true, true, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+    default: issue_row_rs<true, true, true, WIDE, KXB, KXE>(a_row, w_base, d0, d1, d2); break;
+  }
+}
+
+// Look-ahead barrier tests of the issuing thread.  A blocking mbarrier wait costs ~250 cycles even when the phase has
+// long completed, and the tensor pipe's instruction queue is too shallow to cover two of them per input row (measured:
+// 350-1200 idle cycles per row).  So the NEXT row's barriers are tested (mbarrier.test_wait, non-blocking) two thirds
+// through the current row's instructions and the predicates are read after the last third: the latency hides behind
+// MMA issue, and the blocking wait remains only as the fallback.  The predicates live in two PTX registers declared once
+// at kernel scope (inline asm cannot carry a predicate between statements any other way).
+#define DEQSCI_TOK_DECL() asm volatile(".reg .pred tokF, tokE;")
+#define DEQSCI_TOK_TEST(tok, bar, par) \
+  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 " #tok ", [%0], %1;" ::"r"(bar), "r"(par) : "memory")
+#define DEQSCI_TOK_GET(tok, out) asm volatile("selp.u32 %0, 1, 0, " #tok ";" : "=r"(out))
+
 // STATS = true (train-mode BatchNorm): additionally accumulates per-output-channel sum and sum of
 // squares of the values it writes (over valid pixels); every CTA writes its partial to p.stats[cta][128].
 // MODE: issue order, see the constants above (0 output-stationary, 2 accumulator buffers of 192 columns; 1 / 2
@@ -243,6 +271,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
                         const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];          // swizzle atoms need the 1 KB alignment; no slack to
   if ((smem_u32(smem) & 1023u) != 0) __trap();               // realign by hand in mode 2 (227 KB exactly)
+  DEQSCI_TOK_DECL();
   constexpr int kSlots = n_slots(MODE), kWBytes = w_bytes(MODE), kTapBytesB = tap_bytes(MODE);
   uint8_t* w_s = smem;
   uint8_t* a_s = w_s + kWBytes;
@@ -324,13 +353,20 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
       int slot = 0;
       uint32_t sphase = 0;
       uint32_t g0 = 0;               // running output-row count: row g lives in accumulator buffer g % 4
+      bool tok_full = false, tok_tempty = false;     // a look-ahead test of this row's barrier is in tokF / tokE
       for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+        const bool last_item = item + n_pairs >= p.n_pair_items;
         for (int q = 0; q < R + 2; ++q) {
+          uint32_t ok;
           if (q < R) {               // a new output row opens: its buffer must have been drained
             const uint32_t g = g0 + q;
-            mbar_wait(bar_tempty(g & 3), ((g >> 2) & 1) ^ 1);
+            ok = 0;
+            if (tok_tempty) DEQSCI_TOK_GET(tokE, ok);
+            if (!ok) mbar_wait(bar_tempty(g & 3), ((g >> 2) & 1) ^ 1);
           }
-          mbar_wait(bar_full(slot), sphase);
+          ok = 0;
+          if (tok_full) DEQSCI_TOK_GET(tokF, ok);
+          if (!ok) mbar_wait(bar_full(slot), sphase);
           tc_fence_after();
           const uint32_t a_row = a_base + slot * kSlotBytes;
           const uint32_t d0 = tmem_base + ((g0 + q) & 3) * kAccColsRS;
@@ -338,14 +374,21 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
           const uint32_t d2 = tmem_base + ((g0 + q - 2) & 3) * kAccColsRS;
           const int live = (q < R ? 1 : 0) | (q >= 1 && q - 1 < R ? 2 : 0) | (q >= 2 ? 4 : 0);
           constexpr bool H = MODE == 2;      // wide instructions
-          switch (live) {
-            case 1: issue_row_rs<true, false, false, H>(a_row, w_base, d0, d1, d2); break;
-            case 2: issue_row_rs<false, true, false, H>(a_row, w_base, d0, d1, d2); break;
-            case 3: issue_row_rs<true, true, false, H>(a_row, w_base, d0, d1, d2); break;
-            case 4: issue_row_rs<false, false, true, H>(a_row, w_base, d0, d1, d2); break;
-            case 6: issue_row_rs<false, true, true, H>(a_row, w_base, d0, d1, d2); break;
-            default: issue_row_rs<true, true, true, H>(a_row, w_base, d0, d1, d2); break;
+          issue_row_live<H, 0, 2>(live, a_row, w_base, d0, d1, d2);
+          // look ahead: the next input row's barriers (same strip, or row 0 of this pair's next strip)
+          tok_full = tok_tempty = false;
+          if (p.lookahead && !(last_item && q == R + 1)) {
+            const int nslot = slot + 1 == kSlots ? 0 : slot + 1;
+            DEQSCI_TOK_TEST(tokF, bar_full(nslot), nslot == 0 ? sphase ^ 1 : sphase);
+            tok_full = true;
+            const int nq = q == R + 1 ? 0 : q + 1;
+            if (nq < R) {
+              const uint32_t ng = (q == R + 1 ? g0 + R : g0) + nq;
+              DEQSCI_TOK_TEST(tokE, bar_tempty(ng & 3), ((ng >> 2) & 1) ^ 1);
+              tok_tempty = true;
+            }
           }
+          issue_row_live<H, 2, 3>(live, a_row, w_base, d0, d1, d2);
           umma2_commit_mc(bar_empty(slot));                       // the input row is consumed (both CTAs)
           if (q >= 2) umma2_commit_mc(bar_tfull((g0 + q - 2) & 3));   // output row q-2 is complete
           if (++slot == kSlots) { slot = 0; sphase ^= 1; }
@@ -567,6 +610,359 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
   if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
 }
 
+
+// ---- a RUN of consecutive hidden layers in ONE launch ---------------------------------------------------------
+// The per-layer kernel above pays, per layer, the drain of its last tile, the exit, the next grid's prologue (barriers,
+// TMEM, 108 KB of weights per CTA) and a cold input ring -- ~8 us, a third of a layer at batch 1 -- because a CTA fills
+// its SM (227 KB, 512 TMEM columns): programmatic dependent launch cannot overlap two layers.  Here the CTA pairs stay
+// resident for the whole run; barriers, TMEM, the rings and their phases carry over.  The grid-wide dependency between
+// layers becomes a per-strip one: a strip of layer l + 1 needs rows h0 - 1 .. h0 + R of layer l's output, i.e. the same
+// strip and its two neighbours in the frame.  Every strip has a ready flag in global memory; the epilogue publishes
+// "layer l stored" (TMA stores complete -> named barrier of the epilogue warps -> st.release.gpu), the TMA producer
+// acquires the three flags before it loads the strip's rows for layer l + 1.  That wait also covers the write-after-read
+// hazard of the ping-pong planes (a neighbour has read my boundary rows of layer l - 1's output before it publishes
+// layer l, and I overwrite them only after I have seen that flag).  Flags count up from a per-launch epoch, so they are
+// never reset.  Deadlock-free: every wait is on a strictly earlier layer and all CTAs are co-resident (grid <= SMs).
+// Weights of the next layer replace the current ones as soon as the layer's last MMA has retired (bar_wfree, committed
+// by the issuer); the peer CTA reports its half through the leader's bar_wpeer (release / acquire at cluster scope).
+// Issue order, accumulator layout and epilogue are those of MODE 2 above: results are bit-identical to 13 launches.
+constexpr int kMaxChain = 16;
+struct ChainParams {
+  const uint8_t* wimg[kMaxChain];      // per layer: [2 ranks][9 taps][96 rows][128 B]
+  const float* scale[kMaxChain];
+  const float* bias[kMaxChain];
+  int relu[kMaxChain];
+  int n_layers;
+  int NF, Hc, Wc;
+  int tiles_x, strips_y, strip_rows;   // tiles_x == 1 (images of at most 128 pixels per row)
+  long long n_strips, n_pair_items;
+  uint32_t* flags;                     // [n_strips]; value epoch + l + 1 = layer l of this launch is in memory
+  uint32_t epoch;
+  int lookahead;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t target) {   // bounded: a protocol bug traps
+  uint32_t spins = 0;
+  while ((int32_t)(ld_acquire_gpu(p) - target) < 0) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_hidden_chain_kernel(const __grid_constant__ CUtensorMap ld_hi0, const __grid_constant__ CUtensorMap ld_lo0,
+                         const __grid_constant__ CUtensorMap ld_hi1, const __grid_constant__ CUtensorMap ld_lo1,
+                         const __grid_constant__ CUtensorMap st_hi0, const __grid_constant__ CUtensorMap st_lo0,
+                         const __grid_constant__ CUtensorMap st_hi1, const __grid_constant__ CUtensorMap st_lo1,
+                         const __grid_constant__ ChainParams p) {
+  constexpr int MODE = 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  DEQSCI_TOK_DECL();
+  constexpr int kSlots = n_slots(MODE), kWBytes = w_bytes(MODE), kTapBytesB = tap_bytes(MODE);
+  uint8_t* w_s = smem;
+  uint8_t* a_s = w_s + kWBytes;
+  uint8_t* st_s = a_s + kSlots * kSlotBytes;
+  uint8_t* tail = st_s + 8 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);        // [0] w, full[4], empty[4], tfull[4], tempty[4], wfree, wpeer
+  float* aff_s = reinterpret_cast<float*>(tail + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 512);
+
+  pdl_launch_dependents();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_w = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlotsMax + s]); };
+  auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlotsMax + b]); };
+  auto bar_tempty = [&](int b) { return smem_u32(&bars[1 + 2 * kSlotsMax + kAccBufsMax + b]); };
+  // weights travel in three groups (the taps of one ky, 36 KB): group ky is last read by input row R - 1 + ky of a
+  // layer's last strip and first read by input row ky of the next layer's first strip, so each group is replaced two
+  // row times before it is needed and the reload never stalls the tensor pipe
+  constexpr int kBarW = 1 + 2 * kSlotsMax + 2 * kAccBufsMax;
+  auto bar_wg = [&](int g) { return smem_u32(&bars[kBarW + g]); };          // group g of the current layer has landed
+  auto bar_wfree = [&](int g) { return smem_u32(&bars[kBarW + 3 + g]); };   // every MMA reading group g has retired
+  auto bar_wpeer = [&](int g) { return smem_u32(&bars[kBarW + 6 + g]); };   // leader only: the peer's group g has landed
+  constexpr int kGroupBytes = 3 * kTapBytesB;
+  const int n_layers = p.n_layers;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < kAccBufsMax; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 16); }
+    for (int g = 0; g < 3; ++g) { mbar_init(bar_wg(g), 1); mbar_init(bar_wfree(g), 1); mbar_init(bar_wpeer(g), 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  auto load_affine = [&](int l) {      // threads 64..127: {scale, bias} pairs of layer l
+    const int c = threadIdx.x - 64;
+    aff_s[2 * c] = p.scale[l] ? p.scale[l][c] : 1.f;
+    aff_s[2 * c + 1] = p.bias[l] ? p.bias[l][c] : 0.f;
+  };
+  if (threadIdx.x >= 64 && threadIdx.x < 128) load_affine(0);
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), kTmemCols);
+  auto load_weight_group = [&](int l, int g) {     // one thread: this CTA's half of layer l's taps 3g .. 3g + 2
+    mbar_arrive_expect_tx(bar_wg(g), kGroupBytes);
+    const uint8_t* src = p.wimg[l] + (size_t)rank * kWBytes + (size_t)g * kGroupBytes;
+    for (int t = 0; t < 3; ++t)
+      bulk_load_1d(smem_u32(w_s + g * kGroupBytes + t * kTapBytesB), src + (size_t)t * kTapBytesB, kTapBytesB, bar_wg(g));
+  };
+  if (warp == 0 && elect_one_sync()) {
+    for (int g = 0; g < 3; ++g) load_weight_group(0, g);
+    for (int g = 0; g < 3; ++g) mbar_wait(bar_wg(g), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                 // both CTAs: barriers initialised, first weights resident, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int R = p.strip_rows;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own rows) =====================
+    if (elect_one_sync()) {
+      pdl_wait_predecessor();
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int l = 0; l < n_layers; ++l) {
+        const CUtensorMap* m_hi = (l & 1) ? &ld_hi1 : &ld_hi0;
+        const CUtensorMap* m_lo = (l & 1) ? &ld_lo1 : &ld_lo0;
+        for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+          long long sid = 2 * item + rank;
+          if (sid >= p.n_strips) sid = p.n_strips - 1;
+          const Strip s = decode(p, sid);
+          // Weight group ky of the new layer goes in as soon as layer l - 1 lets go of it (bar_wfree): group 0 before
+          // anything that can block, groups 1 and 2 between the first rows -- or, when this CTA has a single strip per
+          // layer, all three before the flags (its layer is finished, the flags are what it waits for).
+          const bool first_item = item == pair, single = pair + n_pairs >= p.n_pair_items;
+          int groups_loaded = 3;
+          if (l > 0 && first_item) {
+            groups_loaded = single ? 3 : 1;
+            for (int g = 0; g < groups_loaded; ++g) {
+              mbar_wait(bar_wfree(g), (l - 1) & 1);
+              load_weight_group(l, g);
+            }
+          }
+          if (l > 0) {                             // layer l - 1 of this strip and of its neighbours in the frame
+            const uint32_t target = p.epoch + (uint32_t)l;
+            const int sy = (int)(sid % p.strips_y);
+            wait_flag(p.flags + sid, target);
+            if (sy > 0) wait_flag(p.flags + sid - 1, target);
+            if (sy < p.strips_y - 1) wait_flag(p.flags + sid + 1, target);
+            fence_proxy_async_all();               // the acquired data is read through the async proxy (TMA)
+          }
+          for (int q = 0; q < R + 2; ++q) {
+            if (q >= 1 && q < 3 && groups_loaded <= q) {
+              mbar_wait(bar_wfree(q), (l - 1) & 1);
+              load_weight_group(l, q);
+            }
+            mbar_wait(bar_empty(slot), phase ^ 1);
+            const uint32_t full_leader = mapa(bar_full(slot), 0);
+            if (leader) mbar_arrive_expect_tx(bar_full(slot), 2 * kTxBytes);
+            const uint32_t dst = smem_u32(a_s + slot * kSlotBytes);
+            tma_load_4d_2cta(dst, m_hi, full_leader, 0, s.w0 - 1, s.h0 - 1 + q, s.nf);
+            tma_load_4d_2cta(dst + kPlaneBytes, m_lo, full_leader, 0, s.w0 - 1, s.h0 - 1 + q, s.nf);
+            if (++slot == kSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (!leader) {
+      // peer CTA: tell the leader's issuer when this CTA's half of a layer's weights has landed
+      if (elect_one_sync()) {
+        const uint32_t wpeer_leader = mapa(bar_wpeer(0), 0);
+        for (int l = 1; l < n_layers; ++l)
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(bar_wg(g), l & 1);
+            mbar_arrive_release_cluster(wpeer_leader + 8 * g);
+          }
+      }
+    } else if (elect_one_sync()) {
+      // ===================== MMA issuer (leader CTA, one thread, for the pair) =====================
+      const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
+      int slot = 0;
+      uint32_t sphase = 0;
+      uint32_t g0 = 0;
+      bool tok_full = false, tok_tempty = false;     // a look-ahead test of this row's barrier is in tokF / tokE
+      for (int l = 0; l < n_layers; ++l) {
+        for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+          const bool last_item = item + n_pairs >= p.n_pair_items;
+          for (int q = 0; q < R + 2; ++q) {
+            if (l > 0 && item == pair && q < 3) {     // input row q is the first to read weight group q of this layer
+              mbar_wait(bar_wg(q), l & 1);
+              mbar_wait_acquire_cluster(bar_wpeer(q), (l - 1) & 1);
+            }
+            uint32_t ok;
+            if (q < R) {
+              const uint32_t g = g0 + q;
+              ok = 0;
+              if (tok_tempty) DEQSCI_TOK_GET(tokE, ok);
+              if (!ok) mbar_wait(bar_tempty(g & 3), ((g >> 2) & 1) ^ 1);
+            }
+            ok = 0;
+            if (tok_full) DEQSCI_TOK_GET(tokF, ok);
+            if (!ok) mbar_wait(bar_full(slot), sphase);
+            tc_fence_after();
+            const uint32_t a_row = a_base + slot * kSlotBytes;
+            const uint32_t d0 = tmem_base + ((g0 + q) & 3) * kAccColsRS;
+            const uint32_t d1 = tmem_base + ((g0 + q - 1) & 3) * kAccColsRS;
+            const uint32_t d2 = tmem_base + ((g0 + q - 2) & 3) * kAccColsRS;
+            const int live = (q < R ? 1 : 0) | (q >= 1 && q - 1 < R ? 2 : 0) | (q >= 2 ? 4 : 0);
+            issue_row_live<true, 0, 2>(live, a_row, w_base, d0, d1, d2);
+            // look ahead: the next input row's barriers (same strip, this pair's next strip, or the next layer's first)
+            tok_full = tok_tempty = false;
+            if (p.lookahead && !(last_item && q == R + 1 && l + 1 == n_layers)) {
+              const int nslot = slot + 1 == kSlots ? 0 : slot + 1;
+              DEQSCI_TOK_TEST(tokF, bar_full(nslot), nslot == 0 ? sphase ^ 1 : sphase);
+              tok_full = true;
+              const int nq = q == R + 1 ? 0 : q + 1;
+              if (nq < R) {
+                const uint32_t ng = (q == R + 1 ? g0 + R : g0) + nq;
+                DEQSCI_TOK_TEST(tokE, bar_tempty(ng & 3), ((ng >> 2) & 1) ^ 1);
+                tok_tempty = true;
+              }
+            }
+            issue_row_live<true, 2, 3>(live, a_row, w_base, d0, d1, d2);
+            umma2_commit_mc(bar_empty(slot));
+            if (q >= 2) umma2_commit_mc(bar_tfull((g0 + q - 2) & 3));
+            // both CTAs: input row R - 1 + ky of the layer's last strip was the last reader of weight group ky
+            if (last_item && l + 1 < n_layers && q >= R - 1) umma2_commit_mc(bar_wfree(q - (R - 1)));
+            if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+          }
+          g0 += R;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int half = e >> 2;
+    const uint32_t stage = smem_u32(st_s + e * kStageBytes);
+    const uint32_t tempty_leader0 = mapa(bar_tempty(0), 0);
+    int buf = 0;
+    uint32_t tphase = 0;
+    // A strip's rows of layer l are in memory once every epilogue warp's TMA stores have completed (wait_group 0 by the
+    // storing lanes), hence the barrier of the 8 warps; then one thread publishes.  sid < 0: nothing to publish, but the
+    // barrier is still taken (the next layer's affine is loaded behind the layer's last one).
+    auto publish_strip = [&](long long sid, int l) {
+      bulk_wait0();
+      fence_proxy_async_all();
+      __threadfence();
+      __syncwarp();
+      named_bar_sync(1, 256);
+      if (e == 0 && sid >= 0 && elect_one_sync()) {
+        __threadfence();
+        st_release_gpu(p.flags + sid, p.epoch + (uint32_t)l + 1u);
+      }
+    };
+    for (int l = 0; l < n_layers; ++l) {
+      const int relu = p.relu[l];
+      const CUtensorMap* o_hi = ((l + 1) & 1) ? &st_hi1 : &st_hi0;
+      const CUtensorMap* o_lo = ((l + 1) & 1) ? &st_lo1 : &st_lo0;
+      const bool publish = l + 1 < n_layers;
+      for (long long item = pair; item < p.n_pair_items; item += n_pairs) {
+        const long long sid = 2 * item + rank;
+        const Strip s = decode(p, sid);
+        for (int j = 0; j < R; ++j) {
+          const int h = s.h0 + j;
+          mbar_wait(bar_tfull(buf), tphase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kAccColsRS;
+          uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            uint32_t acc[16], c1[16];
+            tmem_ld16(t_row + half * 96 + part * 16, acc);
+            tmem_ld16(t_row + 32 + half * 32 + part * 16, c1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float v[2];
+              const float4 sb4 = *reinterpret_cast<const float4*>(aff_s + 2 * (half * 32 + part * 16 + i));
+              const float sb[4] = {sb4.x, sb4.y, sb4.z, sb4.w};
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                float a = fmaf(__uint_as_float(c1[i + u]), kLoInvScale, __uint_as_float(acc[i + u]));
+                a = fmaf(a, sb[2 * u], sb[2 * u + 1]);
+                v[u] = relu ? fmaxf(a, 0.f) : a;
+              }
+              split_f16x2(v[0], v[1], hi_pk[part * 8 + (i >> 1)], lo_pk[part * 8 + (i >> 1)]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (elect_one_sync()) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
+          const uint32_t row_addr = stage + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            const uint32_t* pk = plane == 0 ? hi_pk : lo_pk;
+            bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((q ^ sw) << 4)), "r"(pk[4 * q]),
+                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                           : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (s.real && h < p.Hc) {
+              if (elect_one_sync()) {
+                tma_store_4d(plane == 0 ? o_hi : o_lo, stage, half * 32, s.w0 + quarter * 32, h, s.nf);
+                bulk_commit();
+              }
+            }
+          }
+          if (++buf == kAccBufsMax) { buf = 0; tphase ^= 1; }
+        }
+        // The wait for the stores costs the epilogue warps nothing: the next strip's first accumulator fills only after
+        // three more input rows.  (Publishing one strip late instead -- from the next strip's first tile -- starved the
+        // producer: it wants the flags as soon as it has queued the layer's last row.)
+        if (publish) publish_strip(s.real ? sid : -1, l);
+      }
+      if (publish) {
+        // every epilogue warp is past its last use of layer l's affine (the barrier above): load the next layer's
+        if (threadIdx.x >= 64 && threadIdx.x < 128) load_affine(l + 1);
+        named_bar_sync(1, 256);
+      }
+    }
+    bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
 }  // namespace tc2
 
 // ---- host side -------------------------------------------------------------------------------
@@ -639,6 +1035,8 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
   static const uint32_t lo_mask16 = (uint32_t)env_int("DEQSCI_TC_LO_MASK", 0xFFFF) & 0xFFFFu;
   p.lo_mask = lo_mask16 | (lo_mask16 << 16);
   p.stats = stats;
+  static const int lookahead = env_int("DEQSCI_TC_LOOKAHEAD", 1);
+  p.lookahead = lookahead;
   p.dbg_out_hi = act_out;
   p.dbg_out_lo = act_out + plane_elems;
   CUtensorMap in_hi, in_lo, out_hi, out_lo;
@@ -665,6 +1063,83 @@ int conv_hidden_2cta_launch(const __half* act_in, __half* act_out, long long pla
     else if (issue_mode == 1) DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<false, 1>));
     else DEQSCI_CUDA(launch(tc2::conv_hidden_2cta_kernel<false, 2>));
   }
+  DEQSCI_LAUNCH_CHECK();
+  return DEQSCI_OK;
+}
+
+
+// ---- chained launch: layers [0, n_layers) of a run, ping-pong between two plane pairs -----------------------------
+// True when the run kernel can take this shape: wide issue mode (its weight image layout), one 128-pixel tile per row.
+bool tc2_chain_supported(int NF, int Hc, int Wc, int n_layers) {
+  // OFF by default -- EXPERIMENTAL, NOT PARITY-SAFE (DESIGN.md finding 19): on the B200 a TMA load issued right after
+  // the acquire of a strip's ready flag can still return the row's PREVIOUS contents (the data were stored, completed
+  // and fenced >= 10 us earlier; a 10 us pause after the acquire hides it, fences at any scope do not close it), so a
+  // solve drifts from the per-layer kernels by up to 1e-2.  Kept as the record of that experiment.
+  static const int enabled = env_int("DEQSCI_TC_CHAIN_EXPERIMENTAL", 0);
+  // only while a CTA pair has at most this many 16-row strip pairs per layer (batches of 1-2 measurements of
+  // 256 x 256 x 8): measured on one box, the run kernel is 6 % faster at batch 1, 1.6 % at batch 2, equal at 4 and
+  // 2-3 % SLOWER from batch 8 on, where a kernel boundary is under 2 % of a layer
+  static const int max_rounds = env_int("DEQSCI_TC_CHAIN_MAX_ROUNDS", 1);
+  const long long rounds16 = ((long long)NF * ((Hc + 15) / 16) / 2 + num_sms() / 2 - 1) / (num_sms() / 2);
+  return enabled && rounds16 <= max_rounds && tc2_issue_mode() == 2 && tc2_supported(Hc, Wc) && Wc <= tc2::kTileM &&
+         n_layers >= 2 && n_layers <= tc2::kMaxChain;
+}
+size_t tc2_chain_flag_count(int NF, int Hc) { return (size_t)NF * Hc; }       // upper bound: one strip per image row
+
+// Layer l reads plane pair buf[l & 1] and writes buf[(l + 1) & 1]; the result of the run is in buf[n_layers & 1].
+// flags: device uint32[>= tc2_chain_flag_count], zero-initialised once; *epoch: host counter owned by the caller with
+// the flags (one pair per stream), advanced here; values never need resetting until the counter wraps (handled).
+int conv_hidden_chain_launch(__half* buf0, __half* buf1, long long plane_elems, int n_layers, const uint8_t* const* wimg,
+                             const float* const* scale, const float* const* bias, const int* relu, int NF, int Hc, int Wc,
+                             uint32_t* flags, uint32_t* epoch, cudaStream_t st) {
+  tc2::ChainParams p;
+  memset(&p, 0, sizeof(p));
+  for (int l = 0; l < n_layers; ++l) { p.wimg[l] = wimg[l]; p.scale[l] = scale[l]; p.bias[l] = bias[l]; p.relu[l] = relu[l]; }
+  p.n_layers = n_layers;
+  p.NF = NF; p.Hc = Hc; p.Wc = Wc;
+  p.tiles_x = 1;
+  const int pairs_hw = num_sms() / 2;
+  // Strip height: rounds x (R + 1/2 row of per-strip cost), as for the per-layer kernel -- but a CTA that has ONE strip
+  // per layer sits through the whole store -> flag -> load round trip between two layers (~4 row times), while with two
+  // or more its next strip's inputs were published a strip ago: prefer at least two rounds (batch 1: 4-row strips, two
+  // per CTA, instead of one of 8).  DEQSCI_TC_CHAIN_ROWS=n forces a height.
+  static const int forced_rows = env_int("DEQSCI_TC_CHAIN_ROWS", 0);
+  int R = 1;
+  long long best_cost = -1;
+  for (int r = 16; r >= 1; --r) {
+    const long long strips = (long long)NF * ((Hc + r - 1) / r);
+    const long long rounds = ((strips + 1) / 2 + pairs_hw - 1) / pairs_hw;
+    const long long cost = rounds * (2 * r + 1) + (rounds == 1 ? 8 : 0);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; R = r; }
+  }
+  if (forced_rows > 0 && forced_rows <= 16) R = forced_rows;
+  p.strip_rows = R;
+  p.strips_y = (Hc + R - 1) / R;
+  p.n_strips = (long long)NF * p.strips_y;
+  p.n_pair_items = (p.n_strips + 1) / 2;
+  if (*epoch > (1u << 30)) {            // wrap: start over from zeroed flags (stream-ordered behind earlier launches)
+    DEQSCI_CUDA(cudaMemsetAsync(flags, 0, tc2_chain_flag_count(NF, Hc) * sizeof(uint32_t), st));
+    *epoch = 0;
+  }
+  p.flags = flags;
+  p.epoch = *epoch;
+  static const int lookahead = env_int("DEQSCI_TC_LOOKAHEAD", 1);
+  p.lookahead = lookahead;
+  CUtensorMap m[8];
+  __half* bufs[2] = {buf0, buf1};
+  int rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = make_plane_map(&m[2 * b], bufs[b], 64, NF, Hc, Wc, 64, tc2::kTileM + 2, 1, 128))) return rc;
+    if ((rc = make_plane_map(&m[2 * b + 1], bufs[b] + plane_elems, 64, NF, Hc, Wc, 64, tc2::kTileM + 2, 1, 128))) return rc;
+    if ((rc = make_plane_map(&m[4 + 2 * b], bufs[b], 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
+    if ((rc = make_plane_map(&m[4 + 2 * b + 1], bufs[b] + plane_elems, 64, NF, Hc, Wc, 32, 32, 1, 64))) return rc;
+  }
+  const long long pairs = p.n_pair_items < pairs_hw ? p.n_pair_items : pairs_hw;
+  const int smem = tc2::smem_bytes(2);
+  ProfScope prof(PK_CONV_HIDDEN, st);
+  DEQSCI_CUDA(cudaFuncSetAttribute(tc2::conv_hidden_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DEQSCI_CUDA(launch_pdl(tc2::conv_hidden_chain_kernel, (unsigned)(2 * pairs), tc2::kThreads, smem, st, m[0], m[1], m[2], m[3],
+                         m[4], m[5], m[6], m[7], p));
   DEQSCI_LAUNCH_CHECK();
   return DEQSCI_OK;
 }

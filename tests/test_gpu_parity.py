@@ -412,6 +412,42 @@ def test_driver_equals_python_loop(dev, small_vectors, d, monkeypatch):
         assert not torch.equal(a[0], a[2])       # the continued schedule really changes the result
 
 
+
+@pytest.mark.parametrize("d,shape", [("ffdnet", (1, 256, 256)), ("ffdnet", (3, 64, 192)), ("SimpleCNN", (2, 48, 128))])
+def test_pair_kernel_issue_modes_agree(dev, d, shape, tmp_path):
+    """The pair kernel's issue orders (csrc/conv_tc2.cu; fixed per process, hence subprocesses).  The two row-stationary
+    modes share one accumulation order, so the narrow (DEQSCI_TC_RS=1) and wide (2, the default) instruction shapes
+    must agree BIT FOR BIT -- on single iterate-map calls (fresh plan, reused plan, other data in the workspace) and on
+    a 10-iteration solve; the output-stationary order (DEQSCI_TC_RS=0) adds the two correction products in another order
+    and agrees to fp32 rounding.  Also: the same call twelve times over gives the same bits."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    B, H, W = shape
+    outs = {}
+    for name, env in {"wide": {"DEQSCI_TC_RS": "2"}, "narrow": {"DEQSCI_TC_RS": "1"}, "os": {"DEQSCI_TC_RS": "0"},
+                      "wide_nolook": {"DEQSCI_TC_RS": "2", "DEQSCI_TC_LOOKAHEAD": "0"}}.items():
+        out = str(tmp_path / (name + ".npz"))
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "run_denoiser_once.py"), d, out, str(B), str(H),
+                            str(W)], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = np.load(out)
+    keys = ("f1", "a1", "a2", "b1", "z")
+    report = {n: dict({k: float(np.abs(outs[n][k] - outs["wide"][k]).max()) for k in keys},
+                      rep_maxdiff=float(outs[n]["rep_maxdiff"])) for n in outs}
+    print(report)
+    for n in outs:
+        assert float(outs[n]["rep_maxdiff"]) == 0.0, (n, report)     # the same call again: the same bits
+    for k in keys:
+        assert np.array_equal(outs["narrow"][k], outs["wide"][k]), (k, report)
+        assert np.array_equal(outs["wide_nolook"][k], outs["wide"][k]), (k, report)
+    assert float(outs["narrow"]["res"]) == float(outs["wide"]["res"])
+    assert max(rel_l2(outs["os"][k], outs["wide"][k]) for k in ("f1", "a1", "a2", "b1")) <= 1e-6
+    assert rel_l2(outs["os"]["z"], outs["wide"]["z"]) <= 1e-4
+
+
 def test_per_iterate_trace_vs_oracle(dev, small_vectors):
     """Every iterate of a 12-iteration Anderson run vs the numpy oracle (SimpleCNN weights)."""
     from deqsci_b200.solvers import new_equilibrium_utils_yaping as eq
