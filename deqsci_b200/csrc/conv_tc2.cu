@@ -4,19 +4,26 @@
 // Why a pair: the split-precision weights [Wh | Wl'] of one layer are 144 KB.  Resident in ONE CTA
 // they leave room for only two activation-row slots and no store staging, so the single-CTA kernel
 // (conv_tc.cu, LD_ROW3) is starved by TMA latency and its epilogue pays 32 partial-line stores per
-// instruction.  cta_group::2 lets each CTA of the pair keep HALF of the B operand (72 KB): that
-// frees shared memory for a 4-slot rolling row ring (every input row is loaded once per strip and
-// used by the three output rows around it) plus staging buffers for coalesced TMA stores, and halves
-// the B-operand shared-memory reads per SM.
+// instruction.  cta_group::2 lets each CTA of the pair keep HALF of the B operand (72 KB; 108 KB in
+// the default issue mode): that frees shared memory for a rolling row ring (every input row is loaded
+// once per strip and used by the three output rows around it) plus staging buffers for coalesced TMA
+// stores, and halves the B-operand shared-memory reads per SM.
 //
 // Each CTA of the pair owns its own strip of R consecutive output rows (128-pixel row segments) of
-// some frame; the two strips only share the weights.  Per output row and CTA:
-//     MMA 1: A = Ah (own 128 pixels), B = 128 rows (64 from each CTA), N = 128
-//     MMA 2: A = Al',                 B =  64 rows (32 from each CTA), N =  64
-// B rows are interleaved so both instructions find their half at the SAME smem address in each CTA:
-//     leader tile rows [0,32) = Wh[0:32], [32,64) = Wl'[0:32];  peer: Wh[32:64], Wl'[32:64]
-//   => MMA 1 columns: [0,32) main 0-31 | [32,64) corr1 0-31 | [64,96) main 32-63 | [96,128) corr1 32-63
-//      MMA 2 columns: [128,192) corr2 0-63           out = main + 2^-11 (corr1 + corr2)
+// some frame; the two strips only share the weights.  out = main + 2^-11 (corr1 + corr2) with
+//     main = Ah x Wh,   corr1 = Ah x Wl',   corr2 = Al' x Wh        (three fp16 products per fp32-accurate one)
+//
+// Default issue order (MODE 2, "row-stationary wide"; DESIGN.md finding 17): the issuer walks the strip's R + 2 INPUT
+// rows.  A slice (row q, tap column kx, 16 channels k) of the hi plane is multiplied with the weights of the three output
+// rows it feeds (ky = 0, 1, 2 -> rows q, q-1, q-2) in three consecutive N = 128 instructions (B = [Wh | Wl'], 64 rows from
+// each CTA), the same slice of the lo plane in three N = 64 instructions (B = Wh, 32 rows from each CTA): the A tile is
+// fetched from shared memory once per three instructions (collector hints).  Accumulator of an output row, 128 columns:
+//     [0,32) main 0-31 | [32,96) corr1 + corr2 0-63 | [96,128) main 32-63
+// -- the N = 64 instruction writes the middle 64 columns of the N = 128 one's 128, which fixes the weight-tile layout
+// (tc2_layout below: 96 rows per tap and CTA, one 32-row block of Wh stored twice).  Four accumulators: three rows in
+// flight, one draining.  MODE 1 issues nine N = 64 instructions per slice on the 64-row tiles; MODE 0 is the round-1
+// output-stationary order (per output row: 9 taps x {N = 128 on Ah, N = 64 on Al'}, accumulators of 192 columns: main /
+// corr1 interleaved in [0,128), corr2 in [128,192), added in the epilogue).
 //
 // Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM alloc (+ MMA issuer in the
 // leader CTA only), warps 2-9 epilogue (TMEM lane quarter = warp % 4, channel half = (warp-2) / 4).
@@ -612,6 +619,12 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 
 
 // ---- a RUN of consecutive hidden layers in ONE launch ---------------------------------------------------------
+// EXPERIMENTAL, OFF BY DEFAULT, NOT PARITY-SAFE (DESIGN.md finding 19; DEQSCI_TC_CHAIN_EXPERIMENTAL=1).  Single calls
+// match the per-layer kernel bit for bit, but now and then a TMA load issued right after the acquire of a neighbour's
+// ready flag returns that row's PREVIOUS contents: the hand-off below is the documented pattern (store completion ->
+// proxy fence -> release; acquire -> proxy fence -> TMA load) and still is not coherent on the B200 without a pause
+// after the acquire.  Kept as the record of the experiment and of its measurements.
+//
 // The per-layer kernel above pays, per layer, the drain of its last tile, the exit, the next grid's prologue (barriers,
 // TMEM, 108 KB of weights per CTA) and a cold input ring -- ~8 us, a third of a layer at batch 1 -- because a CTA fills
 // its SM (227 KB, 512 TMEM columns): programmatic dependent launch cannot overlap two layers.  Here the CTA pairs stay
@@ -625,7 +638,7 @@ conv_hidden_2cta_kernel(const __grid_constant__ CUtensorMap in_hi, const __grid_
 // never reset.  Deadlock-free: every wait is on a strictly earlier layer and all CTAs are co-resident (grid <= SMs).
 // Weights of the next layer replace the current ones as soon as the layer's last MMA has retired (bar_wfree, committed
 // by the issuer); the peer CTA reports its half through the leader's bar_wpeer (release / acquire at cluster scope).
-// Issue order, accumulator layout and epilogue are those of MODE 2 above: results are bit-identical to 13 launches.
+// Issue order, accumulator layout and epilogue are those of MODE 2 above.
 constexpr int kMaxChain = 16;
 struct ChainParams {
   const uint8_t* wimg[kMaxChain];      // per layer: [2 ranks][9 taps][96 rows][128 B]
@@ -696,7 +709,6 @@ conv_hidden_chain_kernel(const __grid_constant__ CUtensorMap ld_hi0, const __gri
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_w = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return smem_u32(&bars[1 + s]); };
   auto bar_empty = [&](int s) { return smem_u32(&bars[1 + kSlotsMax + s]); };
   auto bar_tfull = [&](int b) { return smem_u32(&bars[1 + 2 * kSlotsMax + b]); };
@@ -712,7 +724,6 @@ conv_hidden_chain_kernel(const __grid_constant__ CUtensorMap ld_hi0, const __gri
   const int n_layers = p.n_layers;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_w, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < kAccBufsMax; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 16); }
     for (int g = 0; g < 3; ++g) { mbar_init(bar_wg(g), 1); mbar_init(bar_wfree(g), 1); mbar_init(bar_wpeer(g), 1); }
