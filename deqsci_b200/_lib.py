@@ -94,6 +94,7 @@ SIGNATURES = {
     "deqsci_profile_begin": (c_int, [c_int]),
     "deqsci_profile_end": (c_int, [_P, _P, _P]),
     "deqsci_debug_pair_strip_rows": (c_int, [c_int, c_int, c_int, c_int]),
+    "deqsci_debug_pair_weight_map": (ctypes.c_longlong, [_P, ctypes.c_longlong]),
     "deqsci_debug_hidden_layer": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, _P]),
 }
 

@@ -623,6 +623,12 @@ extern "C" int deqsci_debug_pair_strip_rows(int NF, int Hc, int Wc, int n_sms) {
   return pick_strip_rows_balanced(NF, (Wc + 127) / 128, Hc, false, n_sms / 2, 2, 1, 1);
 }
 
+extern "C" long long deqsci_debug_pair_weight_map(int* map, long long count) {
+  const long long n = (long long)(tc2_weight_image_bytes() / 2);
+  if (map && count >= n) tc2_pack_map(map);
+  return n;
+}
+
 // Testing hook (declared in deqsci.h): one hidden 64->64 layer on caller-provided planes.
 extern "C" int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* act_in, void* act_out,
                                          int NF, int Hc, int Wc, void* stream) {

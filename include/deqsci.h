@@ -364,6 +364,12 @@ int deqsci_debug_hidden_layer(const deqsci_denoiser* h, int layer, const void* a
  * suite can pin its choices. */
 int deqsci_debug_pair_strip_rows(int NF, int Hc, int Wc, int num_sms);
 
+/* Testing hook (host only, no device work): the gather map of the CTA-pair hidden kernel's weight image for this
+ * process's issue mode (DEQSCI_TC_RS; csrc/conv_tc2.cu tc2_layout): map[e] = 4 * index into w[64][64][3][3] + kind
+ * (0 = fp16 hi half, 1 = scaled lo half) for every fp16 element e of the image [2 ranks][9 taps][rows][64].  Returns
+ * the number of elements; map may be NULL (or count too small) to query it. */
+long long deqsci_debug_pair_weight_map(int* map, long long count);
+
 #ifdef __cplusplus
 }
 #endif

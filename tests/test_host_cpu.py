@@ -275,3 +275,61 @@ def test_pair_kernel_strip_height_model():
     assert L.deqsci_debug_pair_strip_rows(8, 128, 128, 148) == 8          # batch 1: one round of 8-row strips
     assert L.deqsci_debug_pair_strip_rows(256, 128, 128, 148) == 16       # batch 32
     assert L.deqsci_debug_pair_strip_rows(0, 128, 128, 148) == 0
+
+
+_PAIR_MAP_SCRIPT = r"""
+import ctypes, sys
+import numpy as np
+sys.path.insert(0, %r)
+from deqsci_b200 import _lib
+L = _lib.lib()
+n = L.deqsci_debug_pair_weight_map(None, 0)
+m = np.zeros(n, np.int32)
+assert L.deqsci_debug_pair_weight_map(m.ctypes.data_as(ctypes.c_void_p), n) == n
+np.save(sys.argv[1], m)
+"""
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pair_kernel_weight_tile_layout(mode, tmp_path):
+    """Weight image of the CTA-pair hidden kernel per issue mode (csrc/conv_tc2.cu tc2_layout; host only).  With
+    cta_group::2 an instruction reads its B rows at the SAME offset in both CTAs, first half of the N columns from the
+    leader, second half from the peer.  Modes 0 / 1: 64 rows per tap and CTA, [Wh(32r..) ; Wl'(32r..)].  Mode 2 (default):
+    96 rows; the N = 128 instruction reads rows [32,96) -> columns main 0-31 | corr 0-31 | corr 32-63 | main 32-63, the
+    N = 64 one rows [0,32) -> Wh 0-31 | Wh 32-63, landing on the 64 corr columns in the middle."""
+    import subprocess
+    import sys
+    out = str(tmp_path / "map.npy")
+    env = dict(os.environ, DEQSCI_TC_RS=str(mode))
+    r = subprocess.run([sys.executable, "-c", _PAIR_MAP_SCRIPT % ROOT, out], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = np.load(out)
+    rows = 96 if mode == 2 else 64
+    assert m.size == 2 * 9 * rows * 64
+    img = m.reshape(2, 9, rows, 64)                      # [rank][tap][row][16-byte-chunk-swizzled k]
+
+    def row(rank, tap, n):                               # undo the 128-byte swizzle: element k sits in chunk (k >> 3) ^ (n & 7)
+        k = np.arange(64)
+        return img[rank, tap, n, (((k >> 3) ^ (n & 7)) << 3) + (k & 7)]
+
+    def expect(co, tap, lo):
+        ky, kx = divmod(tap, 3)
+        return (((co * 64 + np.arange(64)) * 3 + ky) * 3 + kx) * 4 + (1 if lo else 0)
+
+    for tap in range(9):
+        if mode == 2:
+            # what the N = 128 instruction sees: leader rows [32,96), then peer rows [32,96)
+            wide = [(0, n) for n in range(32, 96)] + [(1, n) for n in range(32, 96)]
+            cols = [(c, False) for c in range(32)] + [(c, True) for c in range(32)] + \
+                   [(c, True) for c in range(32, 64)] + [(c, False) for c in range(32, 64)]
+            # the N = 64 instruction: leader rows [0,32), peer rows [0,32) -> lands on columns [32,96) of the above
+            narrow = [(0, n) for n in range(32)] + [(1, n) for n in range(32)]
+            for (rank, n), (co, lo) in zip(wide, cols):
+                assert np.array_equal(row(rank, tap, n), expect(co, tap, lo)), (tap, rank, n)
+            for j, (rank, n) in enumerate(narrow):
+                co, lo = cols[32 + j]
+                assert lo and np.array_equal(row(rank, tap, n), expect(co, tap, False)), (tap, rank, n)
+        else:
+            for rank in range(2):
+                for n in range(64):
+                    assert np.array_equal(row(rank, tap, n), expect(32 * rank + (n & 31), tap, n >= 32)), (tap, rank, n)
